@@ -1,0 +1,11 @@
+"""ag-pathtracer_b200: B200-native (sm_100a) implementation of ag-pathtracer's per-pixel
+path-tracing hot path.
+
+Layout: ``csrc/`` CUDA kernels + C ABI (``libagpt.so``), ``host/`` C++ mirror of the reference's
+scene API (``libagpt_host.so``), ``binding.py`` ctypes harness binding.  The directory name has
+a hyphen, so tests and bench load this package through ``importlib`` under the module name
+``agpt_b200`` (see ``tests/conftest.py`` / ``__graft_entry__.py``).
+"""
+from .binding import (AgptError, Context, HostScene, HostTracer, Material, Stats, FLAG_COUNTERS, FLAG_TIMING,  # noqa: F401
+                      FLAG_FAST_BOXES, MAT_DISNEY, MAT_MIRROR, HIT_DTYPE, config_defaults, core, device_count, host,
+                      lib_paths, make_material)

@@ -1,0 +1,335 @@
+"""ctypes binding over the two in-tree shared libraries.
+
+* ``libagpt.so``      -- CUDA kernels behind the C ABI of ``include/agpt.h`` (the product).
+* ``libagpt_host.so`` -- host mirror of the reference's C++ scene API behind ``include/agpt_host.h``.
+
+Python is only the test / benchmark harness language here: the reference is C++, and so is the
+host side of the drop-in.  Nothing in this module computes on the CPU; every ``Context`` method
+is one C-ABI call.  If ``libagpt.so`` is missing or no CUDA device can be opened the calls raise
+``AgptError`` -- there is deliberately no fallback.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+FLAG_COUNTERS = 1
+FLAG_TIMING = 2
+FLAG_FAST_BOXES = 4
+
+MAT_DISNEY = 1
+MAT_MIRROR = 2
+
+
+class AgptError(RuntimeError):
+    pass
+
+
+class Material(ctypes.Structure):  # agpt_material
+    _fields_ = [("type", c_int32), ("lobes", c_uint32), ("roughness", c_float), ("metallic", c_float),
+                ("diffuse_r", c_float * 3), ("eta", c_float), ("spec_r0", c_float * 3), ("alpha_x", c_float),
+                ("mirror_r", c_float * 3), ("alpha_y", c_float)]
+
+
+class Stats(ctypes.Structure):  # agpt_stats
+    _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "node_visits",
+                                         "box_tests", "tri_tests", "analytic_tests", "kernel_launches", "waves")] + \
+               [(n, c_float) for n in ("ms_render", "ms_trace", "ms_shade", "ms_other")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+    @property
+    def rays(self):
+        return self.rays_closest + self.rays_shadow + self.rays_mis
+
+
+HIT_DTYPE = np.dtype([("found", np.uint32), ("prim", np.int32), ("tri", np.int32), ("t", np.float32)])
+
+_core = None
+_host = None
+
+
+def lib_paths():
+    return os.path.join(_HERE, "libagpt.so"), os.path.join(_HERE, "libagpt_host.so")
+
+
+def core():
+    """libagpt.so (loads without a GPU; every compute entry point then fails loudly)."""
+    global _core
+    if _core is None:
+        path = lib_paths()[0]
+        if not os.path.exists(path):
+            raise AgptError(f"{path} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        lib.agpt_last_error.restype = c_char_p
+        _core = lib
+    return _core
+
+
+def host():
+    global _host
+    if _host is None:
+        core()
+        path = lib_paths()[1]
+        if not os.path.exists(path):
+            raise AgptError(f"{path} is not built")
+        lib = ctypes.CDLL(path)
+        lib.agpt_host_last_error.restype = c_char_p
+        _host = lib
+    return _host
+
+
+def _check(rc, lib=None, host_side=False):
+    if rc < 0:
+        msg = (host().agpt_host_last_error() if host_side else core().agpt_last_error()) or b""
+        raise AgptError(f"agpt error {rc}: {msg.decode(errors='replace')}")
+    return rc
+
+
+def _fptr(a):
+    return a.ctypes.data_as(POINTER(c_float))
+
+
+def device_count():
+    n = c_int(0)
+    rc = core().agpt_device_count(byref(n))
+    return n.value if rc == 0 else 0
+
+
+class Context:
+    """agpt_ctx: one per GPU."""
+
+    def __init__(self, device=0):
+        self._h = c_void_p()
+        _check(core().agpt_create(c_int(device), byref(self._h)))
+        self.device = device
+        self.width = self.height = 0
+
+    def close(self):
+        if self._h:
+            core().agpt_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(core().agpt_set_stream(self._h, c_void_p(cuda_stream_ptr)))
+
+    def set_film(self, width, height):
+        _check(core().agpt_set_film(self._h, c_int(width), c_int(height)))
+        self.width, self.height = width, height
+
+    def clear(self):
+        _check(core().agpt_clear(self._h))
+
+    def render(self, first_sample, num_samples, max_depth, depth_arg=0, flags=0, sample_stride=1):
+        _check(core().agpt_render(self._h, c_int(first_sample), c_int(num_samples), c_int(sample_stride),
+                                  c_int(max_depth), c_int(depth_arg), c_uint32(flags)))
+
+    def read_accum(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        _check(core().agpt_read_accum(self._h, _fptr(out)))
+        return out
+
+    def write_accum(self, arr):
+        arr = np.ascontiguousarray(arr, np.float32)
+        assert arr.shape == (self.height, self.width, 4)
+        _check(core().agpt_write_accum(self._h, _fptr(arr)))
+
+    def accum_ptr(self):
+        p = c_void_p()
+        _check(core().agpt_accum_ptr_dev(self._h, byref(p)))
+        return p.value
+
+    def set_accum_dev(self, dev_ptr):
+        _check(core().agpt_set_accum_dev(self._h, c_void_p(dev_ptr)))
+
+    def resolve(self, samples):
+        out = np.empty((self.height, self.width), np.uint32)
+        _check(core().agpt_resolve(self._h, c_int(samples), out.ctypes.data_as(POINTER(c_uint32))))
+        return out
+
+    def trace_primary(self, sample, flags=0):
+        out = np.empty(self.width * self.height, HIT_DTYPE)
+        _check(core().agpt_trace_primary(self._h, c_int(sample), c_uint32(flags), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def trace_rays(self, rays7, any_hit=False, flags=0):
+        rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
+        out = np.empty(len(rays7), HIT_DTYPE)
+        _check(core().agpt_trace_rays(self._h, c_int64(len(rays7)), _fptr(rays7), c_int(1 if any_hit else 0),
+                                      c_uint32(flags), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def li_pixels(self, xs, ys, ss, max_depth, depth_arg=0):
+        xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); ss = np.ascontiguousarray(ss, np.int32)
+        out = np.empty((len(xs), 3), np.float32)
+        ip = lambda a: a.ctypes.data_as(POINTER(c_int))
+        _check(core().agpt_li_pixels(self._h, c_int(len(xs)), ip(xs), ip(ys), ip(ss), c_int(max_depth), c_int(depth_arg), _fptr(out)))
+        return out
+
+    def li_rays(self, rays7, rng_states, max_depth, depth_arg=0):
+        rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
+        rng_states = np.ascontiguousarray(rng_states, np.uint32)
+        out = np.empty((len(rays7), 3), np.float32)
+        _check(core().agpt_li_rays(self._h, c_int(len(rays7)), _fptr(rays7), rng_states.ctypes.data_as(POINTER(c_uint32)),
+                                   c_int(max_depth), c_int(depth_arg), _fptr(out)))
+        return out
+
+    def stats(self):
+        s = Stats()
+        _check(core().agpt_get_stats(self._h, byref(s)))
+        return s
+
+    def reset_stats(self):
+        _check(core().agpt_reset_stats(self._h))
+
+    def scene_bytes(self):
+        b = c_uint64(0)
+        _check(core().agpt_scene_bytes(self._h, byref(b)))
+        return b.value
+
+    # ---- probes -------------------------------------------------------------------------
+    def probe_bounds(self, boxes6, rays7):
+        boxes6 = np.ascontiguousarray(boxes6, np.float32).reshape(-1, 6)
+        rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
+        n = len(boxes6)
+        hit = np.empty(n, np.int32); t = np.empty(n, np.float32)
+        _check(core().agpt_probe_bounds(self._h, c_int(n), _fptr(boxes6), _fptr(rays7), hit.ctypes.data_as(POINTER(c_int)), _fptr(t)))
+        return hit, t
+
+    def probe_bsdf(self, material, in14, skip_specular):
+        in14 = np.ascontiguousarray(in14, np.float32).reshape(-1, 14)
+        out = np.empty((len(in14), 12), np.float32)
+        _check(core().agpt_probe_bsdf(self._h, c_int(len(in14)), byref(material), _fptr(in14), c_int(1 if skip_specular else 0), _fptr(out)))
+        return out
+
+    def probe_sphere_sample(self, in9):
+        in9 = np.ascontiguousarray(in9, np.float32).reshape(-1, 9)
+        out = np.empty((len(in9), 8), np.float32)
+        _check(core().agpt_probe_sphere_sample(self._h, c_int(len(in9)), _fptr(in9), _fptr(out)))
+        return out
+
+    def probe_stream(self, pixel_index, sample, k):
+        out = np.empty(k, np.float32)
+        _check(core().agpt_probe_stream(self._h, c_uint32(pixel_index), c_uint32(sample), c_int(k), _fptr(out)))
+        return out
+
+
+def make_material(mtype, color, roughness=0.0, metallic=0.0):
+    m = Material()
+    col = (c_float * 3)(*[float(v) for v in color])
+    _check(host().agpt_host_make_material(c_int(mtype), col, c_float(roughness), c_float(metallic), byref(m)), host_side=True)
+    return m
+
+
+def config_defaults(config):
+    out = (c_int * 5)()
+    name = c_char_p()
+    _check(host().agpt_host_config_defaults(c_int(config), out, byref(name)), host_side=True)
+    return dict(width=out[0], height=out[1], spp=out[2], max_depth=out[3], depth_arg=out[4], name=name.value.decode())
+
+
+class HostScene:
+    """A BASELINE.json configuration built through the host mirror of the reference API."""
+
+    def __init__(self, config, level=0):
+        self._h = c_void_p()
+        _check(host().agpt_host_scene_create(c_int(config), c_int(level), byref(self._h)), host_side=True)
+        self.config, self.level = config, level
+
+    def close(self):
+        if self._h:
+            host().agpt_host_scene_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def counts(self):
+        c = (c_int64 * 4)(); b = c_uint64(0)
+        _check(host().agpt_host_scene_counts(self._h, c, byref(b)), host_side=True)
+        return dict(prims=c[0], lights=c[1], tris=c[2], nodes=c[3], bytes=b.value)
+
+    def upload(self, ctx):
+        _check(host().agpt_host_scene_upload(self._h, ctx.handle), host_side=True)
+
+    def camera(self):
+        out = np.empty(19, np.float32)
+        _check(host().agpt_host_camera_export(self._h, _fptr(out)), host_side=True)
+        return out
+
+    def prim_info(self, prim):
+        kind = c_int(); counts = (c_int * 5)(); hm = c_int(); il = c_int()
+        _check(host().agpt_host_prim_info(self._h, c_int(prim), byref(kind), counts, byref(hm), byref(il)), host_side=True)
+        return dict(kind=kind.value, nodes=counts[0], tris=counts[1], has_normals=bool(counts[3]), has_uvs=bool(counts[4]),
+                    has_material=bool(hm.value), is_light=bool(il.value))
+
+    def bvh(self, prim):
+        info = self.prim_info(prim)
+        nodes = np.zeros((info["nodes"], 8), np.uint32)
+        order = np.zeros(info["tris"], np.int32)
+        n = _check(host().agpt_host_bvh_export(self._h, c_int(prim), nodes.ctypes.data_as(c_void_p), order.ctypes.data_as(POINTER(c_int))), host_side=True)
+        return nodes[:n], order
+
+    def mesh_verts(self, prim):
+        info = self.prim_info(prim)
+        v = np.zeros((info["tris"], 9), np.float32)
+        _check(host().agpt_host_mesh_export(self._h, c_int(prim), _fptr(v)), host_side=True)
+        return v
+
+    def material(self, prim):
+        out = np.zeros(20, np.float32)
+        _check(host().agpt_host_material_export(self._h, c_int(prim), _fptr(out)), host_side=True)
+        return out
+
+
+class HostTracer:
+    """CudaPathTracer: the reference-facing integrator object (host buffers in and out)."""
+
+    def __init__(self, max_depth=5, device=0):
+        self._h = c_void_p()
+        _check(host().agpt_host_tracer_create(c_int(max_depth), c_int(device), byref(self._h)), host_side=True)
+
+    def close(self):
+        if self._h:
+            host().agpt_host_tracer_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, scene, width, height, accum, first_sample, num_samples, depth_arg=0, flags=0, reupload=False):
+        assert accum.dtype == np.float32 and accum.shape == (height, width, 4) and accum.flags.c_contiguous
+        _check(host().agpt_host_tracer_render(self._h, scene.handle, c_int(width), c_int(height), _fptr(accum), c_int(first_sample),
+                                              c_int(num_samples), c_int(depth_arg), c_uint32(flags), c_int(1 if reupload else 0)), host_side=True)
+        return accum
+
+    def li(self, scene, origin, direction, depth_arg=0):
+        o = (c_float * 3)(*origin); d = (c_float * 3)(*direction); out = (c_float * 3)()
+        _check(host().agpt_host_tracer_li(self._h, scene.handle, o, d, c_int(depth_arg), out), host_side=True)
+        return np.array(list(out), np.float32)

@@ -1,0 +1,713 @@
+// agpt_api.cu -- libagpt.so: the extern "C" boundary of include/agpt.h over the sm_100a
+// wavefront kernels.  Host code here only moves tables into HBM, sizes launches and drives
+// the wave loop; every ray is traced and shaded on the device.  There is no CPU path: if no
+// CUDA device can be opened agpt_create() fails and the caller gets the CUDA error text.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "agpt_kernels.cuh"
+
+// ---- error plumbing ----------------------------------------------------------------------
+static thread_local std::string g_error;
+static int Fail(int code, const std::string& msg) { g_error = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return Fail(AGPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define NEED(cond, code, msg) do { if (!(cond)) return Fail(code, msg); } while (0)
+
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t n = 0;
+	cudaError_t Alloc(size_t count) {
+		Free();
+		if (count == 0) return cudaSuccess;
+		cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+		if (e == cudaSuccess) n = count;
+		return e;
+	}
+	cudaError_t Upload(const T* host, size_t count, cudaStream_t s) {
+		cudaError_t e = Alloc(count);
+		if (e != cudaSuccess || count == 0) return e;
+		return cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s);
+	}
+	void Free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+	size_t Bytes() const { return n * sizeof(T); }
+};
+
+struct MeshStore {
+	DevBuf<float4> nodes, tris, normals;
+	DevBuf<float2> uvs;
+	DevBuf<int> ids;
+	void Free() { nodes.Free(); tris.Free(); normals.Free(); uvs.Free(); ids.Free(); }
+};
+
+struct agpt_ctx {
+	int device = 0;
+	cudaStream_t ownStream = nullptr, stream = nullptr;
+	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
+	int smCount = 0;
+
+	// scene tables
+	std::vector<MeshStore> meshStore;
+	DevBuf<DMesh> meshes;
+	DevBuf<agpt_sphere> spheres;
+	DevBuf<agpt_plane> planes;
+	DevBuf<agpt_prim> prims;
+	DevBuf<agpt_material> mats;
+	DevBuf<agpt_light> lights;
+	std::vector<agpt_prim> hostPrims;
+	std::vector<agpt_light> hostLights;
+	int nMeshes = 0, nSpheres = 0, nPlanes = 0, nMats = 0;
+	agpt_camera cam;
+	bool haveCam = false;
+	int width = 0, height = 0;
+
+	// film
+	DevBuf<float4> accumOwn;
+	float4* accum = nullptr;      // accumOwn.p or caller-owned
+
+	// wavefront state
+	size_t capacity = 0;          // path slots allocated
+	DevBuf<float4> f4[13];
+	DevBuf<int> i32[3];
+	DevBuf<uint32_t> u32[2];
+	DevBuf<int> queues[6];        // closest A/B (2*cap), shadow A/B, active A/B
+	DevBuf<int> counts;           // 2 x 3
+	DevBuf<unsigned long long> traceCounters;   // 4
+	DevBuf<RayCounters> rayCounters;
+	int* hostCounts = nullptr;    // pinned, 3 ints
+
+	agpt_stats stats;
+};
+
+static const size_t kMaxPathsPerBatch = (size_t)1 << 23;   // 8.4 M path slots ~ 1.8 GB of wavefront state
+
+static DScene MakeScene(const agpt_ctx* c) {
+	DScene s;
+	s.prims = c->prims.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
+	s.mats = c->mats.p; s.lights = c->lights.p;
+	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
+	s.width = c->width; s.height = c->height;
+	s.cam = c->cam;
+	return s;
+}
+
+static PathState MakePathState(agpt_ctx* c) {
+	PathState p;
+	p.rayO = c->f4[0].p; p.rayD = c->f4[1].p; p.hitA = c->f4[2].p; p.beta = c->f4[3].p; p.L = c->f4[4].p;
+	p.neeLight = c->f4[5].p; p.neeMis = c->f4[6].p; p.neeBeta = c->f4[7].p;
+	p.shO = c->f4[8].p; p.shD = c->f4[9].p; p.misO = c->f4[10].p; p.misD = c->f4[11].p; p.Lout = c->f4[12].p;
+	p.hitSlot = c->i32[0].p; p.shadowOccluded = c->i32[1].p; p.misPrim = c->i32[2].p;
+	p.rng = c->u32[0].p; p.flags = c->u32[1].p;
+	return p;
+}
+
+static int EnsureCapacity(agpt_ctx* c, size_t paths) {
+	if (paths <= c->capacity) return AGPT_OK;
+	for (auto& b : c->f4) CU(b.Alloc(paths));
+	for (auto& b : c->i32) CU(b.Alloc(paths));
+	for (auto& b : c->u32) CU(b.Alloc(paths));
+	CU(c->queues[0].Alloc(2 * paths)); CU(c->queues[1].Alloc(2 * paths));
+	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths));
+	c->capacity = paths;
+	return AGPT_OK;
+}
+
+static int CheckReady(agpt_ctx* c, bool needFilm) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	NEED(c->prims.n > 0, AGPT_ERR_STATE, "no primitives uploaded (agpt_upload_primitives)");
+	if (needFilm) {
+		NEED(c->width > 0 && c->height > 0, AGPT_ERR_STATE, "film not set (agpt_set_film)");
+		NEED(c->haveCam, AGPT_ERR_STATE, "camera not set (agpt_set_camera)");
+	}
+	// table consistency: every row must point inside its table
+	for (size_t i = 0; i < c->hostPrims.size(); i++) {
+		const agpt_prim& p = c->hostPrims[i];
+		int limit = p.type == AGPT_PRIM_SPHERE ? c->nSpheres : p.type == AGPT_PRIM_PLANE ? c->nPlanes : c->nMeshes;
+		NEED(p.type >= 0 && p.type <= 3 && p.payload >= 0 && p.payload < limit, AGPT_ERR_INVALID, "primitive row points outside its shape table");
+		NEED(p.material < c->nMats, AGPT_ERR_INVALID, "primitive row points outside the material table");
+		NEED(p.area_light < (int)c->hostLights.size(), AGPT_ERR_INVALID, "primitive row points outside the light table");
+	}
+	for (auto& l : c->hostLights)
+		NEED(l.type != AGPT_LIGHT_AREA || (l.prim >= 0 && l.prim < (int)c->hostPrims.size()), AGPT_ERR_INVALID, "area light without a primitive");
+	return AGPT_OK;
+}
+
+static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+extern "C" {
+
+const char* agpt_last_error(void) { return g_error.c_str(); }
+
+int agpt_device_count(int* out) {
+	NEED(out != nullptr, AGPT_ERR_INVALID, "null out");
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { *out = 0; return Fail(AGPT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+	*out = n;
+	return AGPT_OK;
+}
+
+int agpt_create(int device, agpt_ctx** out) {
+	NEED(out != nullptr, AGPT_ERR_INVALID, "null out");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return Fail(AGPT_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+			" (libagpt has no CPU path)");
+	NEED(device >= 0 && device < n, AGPT_ERR_INVALID, "device index out of range");
+	CU(cudaSetDevice(device));
+	agpt_ctx* c = new agpt_ctx();
+	c->device = device;
+	memset(&c->stats, 0, sizeof(c->stats));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	c->smCount = prop.multiProcessorCount;
+	CU(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+	c->stream = c->ownStream;
+	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
+	CU(c->counts.Alloc(6));
+	CU(c->traceCounters.Alloc(4));
+	CU(c->rayCounters.Alloc(1));
+	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
+	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
+	CU(cudaMallocHost((void**)&c->hostCounts, 3 * sizeof(int)));
+	*out = c;
+	return AGPT_OK;
+}
+
+int agpt_destroy(agpt_ctx* c) {
+	if (!c) return AGPT_OK;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto& m : c->meshStore) m.Free();
+	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->mats.Free(); c->lights.Free();
+	c->accumOwn.Free();
+	for (auto& b : c->f4) b.Free();
+	for (auto& b : c->i32) b.Free();
+	for (auto& b : c->u32) b.Free();
+	for (auto& b : c->queues) b.Free();
+	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
+	if (c->hostCounts) cudaFreeHost(c->hostCounts);
+	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
+	cudaStreamDestroy(c->ownStream);
+	delete c;
+	return AGPT_OK;
+}
+
+int agpt_set_stream(agpt_ctx* c, void* s) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	c->stream = s ? (cudaStream_t)s : c->ownStream;
+	return AGPT_OK;
+}
+
+// ---- scene upload ------------------------------------------------------------------------
+int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
+	NEED(c != nullptr && n >= 0 && (n == 0 || meshes != nullptr), AGPT_ERR_INVALID, "bad mesh table");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	for (auto& m : c->meshStore) m.Free();
+	c->meshStore.assign(n, MeshStore());
+	std::vector<DMesh> table(n);
+	for (int i = 0; i < n; i++) {
+		const agpt_mesh_desc& d = meshes[i];
+		NEED(d.n_tris >= 0 && d.n_nodes >= 0 && (d.n_tris == 0 || (d.tri_verts && d.tri_ids)), AGPT_ERR_INVALID, "mesh without triangle data");
+		NEED(d.n_nodes == 0 || (d.nodes != nullptr && d.n_nodes >= 1), AGPT_ERR_INVALID, "mesh node table missing");
+		MeshStore& st = c->meshStore[i];
+		CU(st.nodes.Upload((const float4*)d.nodes, 2 * (size_t)d.n_nodes, c->stream));
+		CU(st.tris.Upload((const float4*)d.tri_verts, 3 * (size_t)d.n_tris, c->stream));
+		CU(st.ids.Upload(d.tri_ids, (size_t)d.n_tris, c->stream));
+		if (d.tri_normals) CU(st.normals.Upload((const float4*)d.tri_normals, 3 * (size_t)d.n_tris, c->stream));
+		if (d.tri_uvs) CU(st.uvs.Upload((const float2*)d.tri_uvs, 3 * (size_t)d.n_tris, c->stream));
+		if (d.n_tris > 0) {
+			k_flag_degenerate<<<Blocks(d.n_tris, 256), 256, 0, c->stream>>>(st.tris.p, st.uvs.p, d.n_tris);
+			CU(cudaGetLastError());
+			c->stats.kernel_launches++;
+		}
+		// interior links and leaf ranges must stay inside the tables
+		for (int k = 0; k < d.n_nodes; k++) {
+			if (k == 1) continue;
+			const agpt_bvh_node& nd = d.nodes[k];
+			if (nd.count > 0) NEED(nd.first >= 0 && nd.first + nd.count <= d.n_tris, AGPT_ERR_INVALID, "BVH leaf range outside the triangle table");
+			else NEED(nd.first >= 2 && nd.first + 1 < d.n_nodes, AGPT_ERR_INVALID, "BVH child link outside the node table");
+		}
+		DMesh& m = table[i];
+		m.nodes = st.nodes.p; m.tris = st.tris.p; m.ids = st.ids.p; m.normals = st.normals.p; m.uvs = st.uvs.p;
+		m.n_nodes = d.n_nodes; m.n_tris = d.n_tris;
+	}
+	CU(c->meshes.Upload(table.data(), (size_t)n, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->nMeshes = n;
+	return AGPT_OK;
+}
+
+#define SIMPLE_UPLOAD(fn, T, member, counter) \
+	int fn(agpt_ctx* c, const T* rows, int n) { \
+		NEED(c != nullptr && n >= 0 && (n == 0 || rows != nullptr), AGPT_ERR_INVALID, "bad table"); \
+		CU(cudaSetDevice(c->device)); \
+		CU(cudaStreamSynchronize(c->stream)); \
+		CU(c->member.Upload(rows, (size_t)n, c->stream)); \
+		CU(cudaStreamSynchronize(c->stream)); \
+		counter; \
+		return AGPT_OK; \
+	}
+SIMPLE_UPLOAD(agpt_upload_spheres, agpt_sphere, spheres, c->nSpheres = n)
+SIMPLE_UPLOAD(agpt_upload_planes, agpt_plane, planes, c->nPlanes = n)
+SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n)
+SIMPLE_UPLOAD(agpt_upload_lights, agpt_light, lights, c->hostLights.assign(rows, rows + n))
+SIMPLE_UPLOAD(agpt_upload_primitives, agpt_prim, prims, c->hostPrims.assign(rows, rows + n))
+
+int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
+	NEED(c != nullptr && cam != nullptr, AGPT_ERR_INVALID, "null camera");
+	c->cam = *cam;
+	c->haveCam = true;
+	return AGPT_OK;
+}
+
+int agpt_set_film(agpt_ctx* c, int width, int height) {
+	NEED(c != nullptr && width > 0 && height > 0 && (long long)width * height < (1ll << 30), AGPT_ERR_INVALID, "bad film size");
+	CU(cudaSetDevice(c->device));
+	if (width == c->width && height == c->height) return AGPT_OK;
+	CU(cudaStreamSynchronize(c->stream));
+	bool own = c->accum == c->accumOwn.p;
+	c->width = width; c->height = height;
+	if (own) {
+		CU(c->accumOwn.Alloc((size_t)width * height));
+		c->accum = c->accumOwn.p;
+		CU(cudaMemsetAsync(c->accum, 0, c->accumOwn.Bytes(), c->stream));
+	}
+	return AGPT_OK;
+}
+
+int agpt_scene_bytes(agpt_ctx* c, uint64_t* out) {
+	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
+	uint64_t b = c->meshes.Bytes() + c->spheres.Bytes() + c->planes.Bytes() + c->prims.Bytes() + c->mats.Bytes() + c->lights.Bytes();
+	for (auto& m : c->meshStore) b += m.nodes.Bytes() + m.tris.Bytes() + m.normals.Bytes() + m.uvs.Bytes() + m.ids.Bytes();
+	*out = b;
+	return AGPT_OK;
+}
+
+// ---- accumulator -------------------------------------------------------------------------
+int agpt_clear(agpt_ctx* c) {
+	NEED(c != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemsetAsync(c->accum, 0, (size_t)c->width * c->height * sizeof(float4), c->stream));
+	return AGPT_OK;
+}
+int agpt_accum_ptr_dev(agpt_ctx* c, void** p) {
+	NEED(c != nullptr && p != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	*p = c->accum;
+	return AGPT_OK;
+}
+int agpt_set_accum_dev(agpt_ctx* c, void* p) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	NEED(c->width > 0, AGPT_ERR_STATE, "film not set");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	if (p) c->accum = (float4*)p;
+	else {
+		if (!c->accumOwn.p) { CU(c->accumOwn.Alloc((size_t)c->width * c->height)); CU(cudaMemset(c->accumOwn.p, 0, c->accumOwn.Bytes())); }
+		c->accum = c->accumOwn.p;
+	}
+	return AGPT_OK;
+}
+int agpt_read_accum(agpt_ctx* c, float* host) {
+	NEED(c != nullptr && host != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemcpyAsync(host, c->accum, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return AGPT_OK;
+}
+int agpt_write_accum(agpt_ctx* c, const float* host) {
+	NEED(c != nullptr && host != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	CU(cudaSetDevice(c->device));
+	CU(cudaMemcpyAsync(c->accum, host, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return AGPT_OK;
+}
+int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
+	NEED(c != nullptr && host != nullptr && c->accum != nullptr && samples > 0, AGPT_ERR_STATE, "film not set or samples <= 0");
+	CU(cudaSetDevice(c->device));
+	int n = c->width * c->height;
+	DevBuf<uint32_t> out;
+	CU(out.Alloc(n));
+	k_resolve<<<Blocks(n, 256), 256, 0, c->stream>>>(c->accum, out.p, n, (float)samples);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(host, out.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	out.Free();
+	return AGPT_OK;
+}
+
+// ---- the wave loop -------------------------------------------------------------------------
+// Runs `n` already-generated paths (slots 0..n-1, queues A filled by k_generate) to completion.
+static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max_depth, int rr_depth_arg, uint32_t flags) {
+	const bool count = flags & AGPT_FLAG_COUNTERS, timing = flags & AGPT_FLAG_TIMING;
+	WaveQueues q[2];
+	for (int k = 0; k < 2; k++) {
+		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
+		q[k].counts = c->counts.p + 3 * k;
+	}
+	int nClosest = n, nShadow = 0, nActive = n, cur = 0;
+	float msTrace = 0, msShade = 0;
+	while (nActive > 0) {
+		if (timing) CU(cudaEventRecord(c->evC, c->stream));
+		if (nClosest > 0) {
+			if (count) k_trace_closest<true><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, c->traceCounters.p);
+			else k_trace_closest<false><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, c->traceCounters.p);
+			c->stats.kernel_launches++;
+		}
+		if (nShadow > 0) {
+			if (count) k_trace_any<true><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, c->traceCounters.p);
+			else k_trace_any<false><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, c->traceCounters.p);
+			c->stats.kernel_launches++;
+		}
+		if (timing) CU(cudaEventRecord(c->evD, c->stream));
+		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
+		ShadeParams sp;
+		sp.count = nActive; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
+		k_shade<<<Blocks(nActive, 128), 128, 0, c->stream>>>(sc, ps, q[cur], q[cur ^ 1], sp, c->rayCounters.p);
+		c->stats.kernel_launches++;
+		CU(cudaGetLastError());
+		if (timing) CU(cudaEventRecord(c->evA, c->stream));
+		CU(cudaMemcpyAsync(c->hostCounts, q[cur ^ 1].counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		if (timing) {
+			float a = 0, b = 0;
+			cudaEventElapsedTime(&a, c->evC, c->evD);
+			cudaEventElapsedTime(&b, c->evD, c->evA);
+			msTrace += a; msShade += b;
+		}
+		nClosest = c->hostCounts[0]; nShadow = c->hostCounts[1]; nActive = c->hostCounts[2];
+		cur ^= 1;
+		c->stats.waves++;
+	}
+	c->stats.ms_trace += msTrace; c->stats.ms_shade += msShade;
+	return AGPT_OK;
+}
+
+int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_stride, int max_depth, int rr_depth_arg, uint32_t flags) {
+	int rcode = CheckReady(c, true);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(num_samples >= 0 && sample_stride >= 1 && max_depth >= 0, AGPT_ERR_INVALID, "bad sample range or depth");
+	NEED(c->accum != nullptr, AGPT_ERR_STATE, "no accumulator");
+	CU(cudaSetDevice(c->device));
+	const size_t wh = (size_t)c->width * c->height;
+	int perBatch = (int)(kMaxPathsPerBatch / wh);
+	if (perBatch < 1) perBatch = 1;
+	if (perBatch > num_samples) perBatch = num_samples;
+	if (num_samples == 0) return AGPT_OK;
+	rcode = EnsureCapacity(c, wh * perBatch);
+	if (rcode != AGPT_OK) return rcode;
+	DScene sc = MakeScene(c);
+	PathState ps = MakePathState(c);
+	WaveQueues q0;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	// evA/evC/evD are reused inside RunWaves when timing; the render bracket has its own pair
+	cudaEvent_t r0, r1;
+	CU(cudaEventCreate(&r0)); CU(cudaEventCreate(&r1));
+	CU(cudaEventRecord(r0, c->stream));
+	for (int done = 0; done < num_samples; done += perBatch) {
+		int ns = num_samples - done < perBatch ? num_samples - done : perBatch;
+		int n = (int)(wh * ns);
+		GenParams g;
+		memset(&g, 0, sizeof(g));
+		g.n = n; g.first_sample = first_sample + done * sample_stride; g.sample_stride = sample_stride;
+		k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
+		CU(cudaGetLastError());
+		c->stats.kernel_launches++;
+		c->stats.paths += (uint64_t)n;
+		c->stats.rays_closest += (uint64_t)n;     // camera rays; the rest is counted on the device
+		rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, flags);
+		if (rcode != AGPT_OK) { cudaEventDestroy(r0); cudaEventDestroy(r1); return rcode; }
+		k_accumulate<<<Blocks(wh, 256), 256, 0, c->stream>>>(ps.Lout, c->accum, c->width, c->height, ns);
+		CU(cudaGetLastError());
+		c->stats.kernel_launches++;
+	}
+	CU(cudaEventRecord(r1, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, r0, r1);
+	cudaEventDestroy(r0); cudaEventDestroy(r1);
+	c->stats.ms_render += ms;
+	return AGPT_OK;
+}
+
+static int TraceTable(agpt_ctx* c, const DScene& sc, const float4* rayO, const float4* rayD, int n, int any_hit, uint32_t flags, agpt_hit* out_host) {
+	DevBuf<agpt_hit> out;
+	CU(out.Alloc(n));
+	const bool count = flags & AGPT_FLAG_COUNTERS;
+	int blocks = Blocks(n, AGPT_TRACE_THREADS);
+	if (any_hit) {
+		if (count) k_trace_table<true, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
+		else k_trace_table<true, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
+	}
+	else {
+		if (count) k_trace_table<false, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
+		else k_trace_table<false, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
+	}
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(out_host, out.p, (size_t)n * sizeof(agpt_hit), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	out.Free();
+	return AGPT_OK;
+}
+
+int agpt_trace_primary(agpt_ctx* c, int sample, uint32_t flags, agpt_hit* out_host) {
+	int rcode = CheckReady(c, true);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(out_host != nullptr, AGPT_ERR_INVALID, "null output");
+	CU(cudaSetDevice(c->device));
+	const size_t wh = (size_t)c->width * c->height;
+	rcode = EnsureCapacity(c, wh);
+	if (rcode != AGPT_OK) return rcode;
+	DScene sc = MakeScene(c);
+	PathState ps = MakePathState(c);
+	WaveQueues q0;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	GenParams g;
+	memset(&g, 0, sizeof(g));
+	g.n = (int)wh; g.first_sample = sample; g.sample_stride = 1;
+	k_generate<<<Blocks(wh, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	return TraceTable(c, sc, ps.rayO, ps.rayD, (int)wh, 0, flags, out_host);
+}
+
+int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uint32_t flags, agpt_hit* out_host) {
+	int rcode = CheckReady(c, false);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(n >= 0 && n < (1ll << 30) && (n == 0 || (rays7 && out_host)), AGPT_ERR_INVALID, "bad ray table");
+	if (n == 0) return AGPT_OK;
+	CU(cudaSetDevice(c->device));
+	// same normalisation as the Ray constructor, done on the device by k_generate
+	rcode = EnsureCapacity(c, (size_t)n);
+	if (rcode != AGPT_OK) return rcode;
+	DScene sc = MakeScene(c);
+	PathState ps = MakePathState(c);
+	WaveQueues q0;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	DevBuf<float> rays;
+	DevBuf<uint32_t> seeds;
+	CU(rays.Upload(rays7, 7 * (size_t)n, c->stream));
+	CU(seeds.Alloc((size_t)n));
+	CU(cudaMemsetAsync(seeds.p, 0, seeds.Bytes(), c->stream));
+	GenParams g;
+	memset(&g, 0, sizeof(g));
+	g.n = (int)n; g.rays7 = rays.p; g.seeds = seeds.p;
+	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	rcode = TraceTable(c, sc, ps.rayO, ps.rayD, (int)n, any_hit, flags, out_host);
+	rays.Free(); seeds.Free();
+	return rcode;
+}
+
+static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, float* out_rgb) {
+	int n = g.n;
+	int rcode = EnsureCapacity(c, (size_t)n);
+	if (rcode != AGPT_OK) return rcode;
+	DScene sc = MakeScene(c);
+	PathState ps = MakePathState(c);
+	WaveQueues q0;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	c->stats.paths += (uint64_t)n;
+	c->stats.rays_closest += (uint64_t)n;
+	rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, 0);
+	if (rcode != AGPT_OK) return rcode;
+	std::vector<float4> host(n);
+	CU(cudaMemcpyAsync(host.data(), ps.Lout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	for (int i = 0; i < n; i++) { out_rgb[3 * i] = host[i].x; out_rgb[3 * i + 1] = host[i].y; out_rgb[3 * i + 2] = host[i].z; }
+	return AGPT_OK;
+}
+
+int agpt_li_pixels(agpt_ctx* c, int n, const int* xs, const int* ys, const int* ss, int max_depth, int rr_depth_arg, float* out_rgb) {
+	int rcode = CheckReady(c, true);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(n >= 0 && (n == 0 || (xs && ys && ss && out_rgb)), AGPT_ERR_INVALID, "bad pixel list");
+	if (n == 0) return AGPT_OK;
+	CU(cudaSetDevice(c->device));
+	DevBuf<int> dx, dy, ds;
+	CU(dx.Upload(xs, n, c->stream)); CU(dy.Upload(ys, n, c->stream)); CU(ds.Upload(ss, n, c->stream));
+	GenParams g;
+	memset(&g, 0, sizeof(g));
+	g.n = n; g.xs = dx.p; g.ys = dy.p; g.ss = ds.p;
+	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
+	dx.Free(); dy.Free(); ds.Free();
+	return rcode;
+}
+
+int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_states, int max_depth, int rr_depth_arg, float* out_rgb) {
+	int rcode = CheckReady(c, false);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(n >= 0 && (n == 0 || (rays7 && rng_states && out_rgb)), AGPT_ERR_INVALID, "bad ray list");
+	if (n == 0) return AGPT_OK;
+	CU(cudaSetDevice(c->device));
+	DevBuf<float> rays;
+	DevBuf<uint32_t> seeds;
+	CU(rays.Upload(rays7, 7 * (size_t)n, c->stream));
+	CU(seeds.Upload(rng_states, (size_t)n, c->stream));
+	GenParams g;
+	memset(&g, 0, sizeof(g));
+	g.n = n; g.rays7 = rays.p; g.seeds = seeds.p;
+	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
+	rays.Free(); seeds.Free();
+	return rcode;
+}
+
+// ---- observability -----------------------------------------------------------------------
+int agpt_get_stats(agpt_ctx* c, agpt_stats* out) {
+	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	unsigned long long tc[4];
+	RayCounters rc;
+	CU(cudaMemcpy(tc, c->traceCounters.p, sizeof(tc), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(&rc, c->rayCounters.p, sizeof(rc), cudaMemcpyDeviceToHost));
+	*out = c->stats;
+	out->node_visits = tc[0]; out->box_tests = tc[1]; out->tri_tests = tc[2]; out->analytic_tests = tc[3];
+	out->rays_closest += rc.rays_closest; out->rays_shadow = rc.rays_shadow; out->rays_mis = rc.rays_mis; out->rays_skip = rc.rays_skip;
+	out->ms_other = out->ms_render - out->ms_trace - out->ms_shade;
+	return AGPT_OK;
+}
+int agpt_reset_stats(agpt_ctx* c) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	memset(&c->stats, 0, sizeof(c->stats));
+	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
+	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
+	return AGPT_OK;
+}
+
+} // extern "C"
+
+// ---- per-function probes -------------------------------------------------------------------
+__global__ void k_probe_bounds(int n, const float* boxes6, const float* rays7, int* out_hit, float* out_t) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* b = boxes6 + 6 * i;
+	const float* r = rays7 + 7 * i;
+	float t = 0;
+	bool h = BoundsIntersect(f3(b[0], b[1], b[2]), f3(b[3], b[4], b[5]), f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]), r[6], t);
+	out_hit[i] = h ? 1 : 0;
+	out_t[i] = h ? t : 0.f;
+}
+
+__global__ void k_probe_bsdf(int n, agpt_material mat, const float* in14, int skipSpecular, float* out12) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* a = in14 + 14 * i;
+	float3 dpdu = f3(a[0], a[1], a[2]), dpdv = f3(a[3], a[4], a[5]), wo = f3(a[6], a[7], a[8]), wi = f3(a[9], a[10], a[11]);
+	float2 u = make_float2(a[12], a[13]);
+	DSurface si;
+	SurfaceInit(si, f3(0.f), dpdu, dpdv);
+	DBSDF bsdf = MakeBSDF(si, &mat);
+	float* o = out12 + 12 * i;
+	float3 f = BSDF_f(bsdf, wo, wi, skipSpecular != 0);
+	o[0] = f.x; o[1] = f.y; o[2] = f.z;
+	o[3] = BSDF_Pdf(bsdf, wo, wi, skipSpecular != 0);
+	float3 wis = f3(0.f);
+	float pdf = 0;
+	bool spec = false;
+	float3 fs = BSDF_Sample_f(bsdf, wo, &wis, u, &pdf, skipSpecular != 0, &spec);
+	o[4] = wis.x; o[5] = wis.y; o[6] = wis.z; o[7] = fs.x; o[8] = fs.y; o[9] = fs.z; o[10] = pdf; o[11] = spec ? 1.f : 0.f;
+}
+
+__global__ void k_probe_sphere_sample(int n, const float* in9, float* out8) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* a = in9 + 9 * i;
+	agpt_sphere s;
+	s.center[0] = a[0]; s.center[1] = a[1]; s.center[2] = a[2]; s.r = a[3]; s.r2 = a[3] * a[3];
+	float3 p, nn;
+	float pdf = 0;
+	SphereSampleFrom(s, f3(a[4], a[5], a[6]), make_float2(a[7], a[8]), &p, &nn, &pdf);
+	float* o = out8 + 8 * i;
+	o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = nn.x; o[4] = nn.y; o[5] = nn.z; o[6] = pdf;
+	o[7] = SpherePdfFrom(s, f3(a[4], a[5], a[6]));
+}
+
+__global__ void k_probe_stream(uint32_t pixel, uint32_t sample, int k, float* out) {
+	uint32_t s = StreamSeed(pixel, sample);
+	for (int i = 0; i < k; i++) out[i] = RandomFloat(s);
+}
+
+template <typename TIn, typename TOut, typename Launch>
+static int ProbeRun(agpt_ctx* c, const TIn* in, size_t nIn, TOut* out, size_t nOut, Launch launch) {
+	DevBuf<TIn> din;
+	DevBuf<TOut> dout;
+	CU(din.Upload(in, nIn, c->stream));
+	CU(dout.Alloc(nOut));
+	launch(din.p, dout.p);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(out, dout.p, nOut * sizeof(TOut), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	din.Free(); dout.Free();
+	return AGPT_OK;
+}
+
+extern "C" {
+
+int agpt_probe_bounds(agpt_ctx* c, int n, const float* boxes6, const float* rays7, int* out_hit, float* out_t) {
+	NEED(c != nullptr && n > 0 && boxes6 && rays7 && out_hit && out_t, AGPT_ERR_INVALID, "bad probe arguments");
+	CU(cudaSetDevice(c->device));
+	DevBuf<float> db, dr, dt;
+	DevBuf<int> dh;
+	CU(db.Upload(boxes6, 6 * (size_t)n, c->stream)); CU(dr.Upload(rays7, 7 * (size_t)n, c->stream));
+	CU(dh.Alloc(n)); CU(dt.Alloc(n));
+	k_probe_bounds<<<Blocks(n, 128), 128, 0, c->stream>>>(n, db.p, dr.p, dh.p, dt.p);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(out_hit, dh.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(out_t, dt.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	db.Free(); dr.Free(); dt.Free(); dh.Free();
+	return AGPT_OK;
+}
+
+int agpt_probe_bsdf(agpt_ctx* c, int n, const agpt_material* mat, const float* in14, int skip_specular, float* out12) {
+	NEED(c != nullptr && n > 0 && mat && in14 && out12, AGPT_ERR_INVALID, "bad probe arguments");
+	CU(cudaSetDevice(c->device));
+	agpt_material m = *mat;
+	return ProbeRun(c, in14, 14 * (size_t)n, out12, 12 * (size_t)n, [&](const float* din, float* dout) {
+		k_probe_bsdf<<<Blocks(n, 128), 128, 0, c->stream>>>(n, m, din, skip_specular, dout);
+	});
+}
+
+int agpt_probe_sphere_sample(agpt_ctx* c, int n, const float* in9, float* out8) {
+	NEED(c != nullptr && n > 0 && in9 && out8, AGPT_ERR_INVALID, "bad probe arguments");
+	CU(cudaSetDevice(c->device));
+	return ProbeRun(c, in9, 9 * (size_t)n, out8, 8 * (size_t)n, [&](const float* din, float* dout) {
+		k_probe_sphere_sample<<<Blocks(n, 128), 128, 0, c->stream>>>(n, din, dout);
+	});
+}
+
+int agpt_probe_stream(agpt_ctx* c, uint32_t pixel_index, uint32_t sample, int k, float* out) {
+	NEED(c != nullptr && k > 0 && out, AGPT_ERR_INVALID, "bad probe arguments");
+	CU(cudaSetDevice(c->device));
+	DevBuf<float> d;
+	CU(d.Alloc(k));
+	k_probe_stream<<<1, 1, 0, c->stream>>>(pixel_index, sample, k, d.p);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(out, d.p, k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	d.Free();
+	return AGPT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,415 @@
+// agpt_bsdf.cuh -- surface interaction, BSDF (Disney diffuse/retro + Trowbridge-Reitz
+// microfacet, mirror) and light sampling on the device, restated from the reference in its
+// operation order.  No virtual dispatch: a material is a 64-byte record whose lobe set is a
+// bit mask in BSDF::bxdfs[] order (diffuse, retro, microfacet | specular), material.h:51-58.
+#pragma once
+
+#include "agpt_device.cuh"
+
+// ---------------------------------------------------------------------------------------
+// shading-space helpers (microfacet.h:3-32)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float CosTheta(float3 w) { return w.z; }
+__device__ __forceinline__ float Cos2Theta(float3 w) { return w.z * w.z; }
+__device__ __forceinline__ float AbsCosTheta(float3 w) { return fabsf(w.z); }
+__device__ __forceinline__ float Sin2Theta(float3 w) { return smax(0.f, 1.f - Cos2Theta(w)); }
+__device__ __forceinline__ float SinTheta(float3 w) { return sqrtf(Sin2Theta(w)); }
+__device__ __forceinline__ float TanTheta(float3 w) { return SinTheta(w) / CosTheta(w); }
+__device__ __forceinline__ float Tan2Theta(float3 w) { return Sin2Theta(w) / Cos2Theta(w); }
+__device__ __forceinline__ float CosPhi(float3 w) { float s = SinTheta(w); return (s == 0) ? 1 : rclamp(w.x / s, -1.f, 1.f); }
+__device__ __forceinline__ float SinPhi(float3 w) { float s = SinTheta(w); return (s == 0) ? 0 : rclamp(w.y / s, -1.f, 1.f); }
+__device__ __forceinline__ float Cos2Phi(float3 w) { return CosPhi(w) * CosPhi(w); }
+__device__ __forceinline__ float Sin2Phi(float3 w) { return SinPhi(w) * SinPhi(w); }
+__device__ __forceinline__ bool SameHemisphere(float3 w, float3 wp) { return w.z * wp.z > 0; }   // precomp.h:713
+
+// ---------------------------------------------------------------------------------------
+// sampling helpers (common.h:84-89,118-143,153-169)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ConcentricSampleDisk(float2 u) {
+	float2 o = make_float2(2.f * u.x - 1, 2.f * u.y - 1);
+	if (o.x == 0 && o.y == 0) return make_float2(0, 0);
+	float theta, r;
+	if (fabsf(o.x) > fabsf(o.y)) { r = o.x; theta = (AGPT_PI / 4) * (o.y / o.x); }
+	else { r = o.y; theta = (AGPT_PI / 2) - (AGPT_PI / 4) * (o.x / o.y); }
+	float st, ct;
+	rsincos(theta, &st, &ct);
+	return make_float2(r * ct, r * st);
+}
+__device__ __forceinline__ float3 CosineSampleHemisphere(float2 u) {
+	float2 d = ConcentricSampleDisk(u);
+	float z = sqrtf(smax(0.f, 1 - d.x * d.x - d.y * d.y));
+	return f3(d.x, d.y, z);
+}
+__device__ __forceinline__ float3 SphericalDirection(float sinTheta, float cosTheta, float phi, float3 x, float3 y, float3 z) {
+	float sp, cp;
+	rsincos(phi, &sp, &cp);
+	return sinTheta * cp * x + sinTheta * sp * y + cosTheta * z;
+}
+__device__ __forceinline__ float3 RandomInSphereU(float2 u) {   // common.h:84-89
+	float a = 1 - 2 * u.x;
+	float b = sqrtf(1 - a * a);
+	float phi = 2 * AGPT_PI * u.y;
+	float sp, cp;
+	rsincos(phi, &sp, &cp);
+	return f3(b * cp, b * sp, a);
+}
+__device__ __forceinline__ float UniformConePdf(float cosThetaMax) { return 1 / (2 * AGPT_PI * (1 - cosThetaMax)); }
+
+// ---------------------------------------------------------------------------------------
+// Fresnel / Disney terms (microfacet.h:180-201, disney.h:12-22,62-71)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float FrDielectric(float cosThetaI, float etaI, float etaT) {
+	cosThetaI = rclamp(cosThetaI, -1.f, 1.f);
+	bool entering = cosThetaI > 0.f;
+	if (!entering) { float t = etaI; etaI = etaT; etaT = t; cosThetaI = fabsf(cosThetaI); }
+	float sinThetaI = sqrtf(smax(0.f, 1.f - cosThetaI * cosThetaI));
+	float sinThetaT = etaI / etaT * sinThetaI;
+	if (sinThetaT >= 1) return 1;
+	float cosThetaT = sqrtf(smax(0.f, 1.f - sinThetaT * sinThetaT));
+	float Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+	float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+	return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+__device__ __forceinline__ float SchlickWeight(float cosTheta) {
+	float m = rclamp(1 - cosTheta, 0.f, 1.f);
+	return (m * m) * (m * m) * m;
+}
+__device__ __forceinline__ float3 FrSchlick(float3 R0, float cosTheta) { return Lerp(SchlickWeight(cosTheta), R0, f3(1.f)); }
+__device__ __forceinline__ float3 DisneyFresnel(const agpt_material& m, float cosI) {
+	return Lerp(m.metallic, f3(FrDielectric(cosI, 1, m.eta)), FrSchlick(f3(m.spec_r0), cosI));
+}
+
+// ---------------------------------------------------------------------------------------
+// Trowbridge-Reitz distribution (microfacet.h:34-153) with Disney's separable G (disney.h:73-82)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float TR_D(float ax, float ay, float3 wh) {
+	float tan2Theta = Tan2Theta(wh);
+	if (isinf(tan2Theta)) return 0.;
+	const float cos4Theta = Cos2Theta(wh) * Cos2Theta(wh);
+	float e = (Cos2Phi(wh) / (ax * ax) + Sin2Phi(wh) / (ay * ay)) * tan2Theta;
+	return 1 / (AGPT_PI * ax * ay * cos4Theta * (1 + e) * (1 + e));
+}
+__device__ __forceinline__ float TR_Lambda(float ax, float ay, float3 w) {
+	float absTanTheta = fabsf(TanTheta(w));
+	if (isinf(absTanTheta)) return 0.f;
+	float alpha = sqrtf(Cos2Phi(w) * ax * ax + Sin2Phi(w) * ay * ay);
+	float alpha2Tan2Theta = (alpha * absTanTheta) * (alpha * absTanTheta);
+	return (-1 + sqrtf(1.f + alpha2Tan2Theta)) / 2;
+}
+__device__ __forceinline__ float TR_G1(float ax, float ay, float3 w) { return 1 / (1 + TR_Lambda(ax, ay, w)); }
+__device__ __forceinline__ float TR_Pdf(float ax, float ay, float3 wo, float3 wh) {
+	return TR_D(ax, ay, wh) * TR_G1(ax, ay, wo) * absdot(wo, wh) / AbsCosTheta(wo);
+}
+__device__ __forceinline__ void TrowbridgeReitzSample11(float cosTheta, float U1, float U2, float* slope_x, float* slope_y) {
+	if (cosTheta > .9999f) {
+		float r = sqrtf(U1 / (1 - U1));
+		float phi = 6.28318530718f * U2;
+		float sp, cp;
+		rsincos(phi, &sp, &cp);
+		*slope_x = r * cp;
+		*slope_y = r * sp;
+		return;
+	}
+	float sinTheta = sqrtf(smax(0.f, 1.f - cosTheta * cosTheta));
+	float tanTheta = sinTheta / cosTheta;
+	float a = 1 / tanTheta;
+	float G1 = 2 / (1 + sqrtf(1.f + 1.f / (a * a)));
+	float A = 2 * U1 / G1 - 1;
+	float tmp = 1.f / (A * A - 1.f);
+	if ((double)tmp > 1e10) tmp = 1e10f;
+	float B = tanTheta;
+	float D = sqrtf(smax(B * B * tmp * tmp - (A * A - B * B) * tmp, 0.f));
+	float slope_x_1 = B * tmp - D;
+	float slope_x_2 = B * tmp + D;
+	*slope_x = (A < 0 || slope_x_2 > 1.f / tanTheta) ? slope_x_1 : slope_x_2;
+	float S;
+	if (U2 > 0.5f) { S = 1.f; U2 = 2.f * (U2 - .5f); }
+	else { S = -1.f; U2 = 2.f * (.5f - U2); }
+	float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) /
+		(U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+	*slope_y = S * z * sqrtf(1.f + *slope_x * *slope_x);
+}
+__device__ __forceinline__ float3 TrowbridgeReitzSample(float3 wi, float ax, float ay, float U1, float U2) {
+	float3 wiS = normalize(f3(ax * wi.x, ay * wi.y, wi.z));
+	float sx, sy;
+	TrowbridgeReitzSample11(CosTheta(wiS), U1, U2, &sx, &sy);
+	float tmp = CosPhi(wiS) * sx - SinPhi(wiS) * sy;
+	sy = SinPhi(wiS) * sx + CosPhi(wiS) * sy;
+	sx = tmp;
+	sx = ax * sx;
+	sy = ay * sy;
+	return normalize(f3(-sx, -sy, 1.f));
+}
+__device__ __forceinline__ float3 TR_Sample_wh(float ax, float ay, float3 wo, float2 u) {
+	bool flip = wo.z < 0;
+	float3 wh = TrowbridgeReitzSample(flip ? -wo : wo, ax, ay, u.x, u.y);
+	if (flip) wh = -wh;
+	return wh;
+}
+
+// ---------------------------------------------------------------------------------------
+// lobes (disney.h:24-60, reflection.h:5-78, reflection.cpp:13-17)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 DisneyDiffuse_f(const agpt_material& m, float3 wo, float3 wi) {
+	float Fo = SchlickWeight(AbsCosTheta(wo)), Fi = SchlickWeight(AbsCosTheta(wi));
+	return f3(m.diffuse_r) * AGPT_INVPI * (1 - Fo / 2) * (1 - Fi / 2);
+}
+__device__ __forceinline__ float3 DisneyRetro_f(const agpt_material& m, float3 wo, float3 wi) {
+	float3 wh = wi + wo;
+	if (wh.x == 0 && wh.y == 0 && wh.z == 0) return f3(0.f);
+	wh = normalize(wh);
+	float cosThetaD = dot(wi, wh);
+	float Fo = SchlickWeight(AbsCosTheta(wo)), Fi = SchlickWeight(AbsCosTheta(wi));
+	float Rr = 2 * m.roughness * cosThetaD * cosThetaD;
+	return f3(m.diffuse_r) * AGPT_INVPI * Rr * (Fo + Fi + Fo * Fi * (Rr - 1));
+}
+__device__ __forceinline__ float3 Microfacet_f(const agpt_material& m, float3 wo, float3 wi) {
+	float cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+	float3 wh = wi + wo;
+	if (cosThetaI == 0 || cosThetaO == 0) return f3(0.f);
+	if (wh.x == 0 && wh.y == 0 && wh.z == 0) return f3(0.f);
+	wh = normalize(wh);
+	float3 F = DisneyFresnel(m, dot(wi, Faceforward(wh, f3(0, 0, 1))));
+	float G = TR_G1(m.alpha_x, m.alpha_y, wo) * TR_G1(m.alpha_x, m.alpha_y, wi);
+	return f3(1.f) * TR_D(m.alpha_x, m.alpha_y, wh) * G * F / (4 * cosThetaI * cosThetaO);
+}
+__device__ __forceinline__ float Microfacet_Pdf(const agpt_material& m, float3 wo, float3 wi) {
+	if (!SameHemisphere(wo, wi)) return 0;
+	float3 wh = normalize(wo + wi);
+	return TR_Pdf(m.alpha_x, m.alpha_y, wo, wh) / (4 * dot(wo, wh));
+}
+__device__ __forceinline__ float Cosine_Pdf(float3 wo, float3 wi) { return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * AGPT_INVPI : 0; }
+
+// lobe order of BSDF::bxdfs[] for a material (material.h:51-58,79-81)
+__device__ __forceinline__ int LobeList(const agpt_material& m, bool skipSpecular, int* lobes) {
+	int n = 0;
+	if (m.lobes & AGPT_LOBE_DIFFUSE) lobes[n++] = AGPT_LOBE_DIFFUSE;
+	if (m.lobes & AGPT_LOBE_RETRO) lobes[n++] = AGPT_LOBE_RETRO;
+	if (m.lobes & AGPT_LOBE_MICROFACET) lobes[n++] = AGPT_LOBE_MICROFACET;
+	if ((m.lobes & AGPT_LOBE_SPECULAR) && !skipSpecular) lobes[n++] = AGPT_LOBE_SPECULAR;
+	return n;
+}
+__device__ __forceinline__ float3 Lobe_f(const agpt_material& m, int lobe, float3 wo, float3 wi) {
+	switch (lobe) {
+	case AGPT_LOBE_DIFFUSE: return DisneyDiffuse_f(m, wo, wi);
+	case AGPT_LOBE_RETRO: return DisneyRetro_f(m, wo, wi);
+	case AGPT_LOBE_MICROFACET: return Microfacet_f(m, wo, wi);
+	default: return f3(0.f);   // SpecularReflection::f (reflection.h:26-28)
+	}
+}
+__device__ __forceinline__ float Lobe_Pdf(const agpt_material& m, int lobe, float3 wo, float3 wi) {
+	switch (lobe) {
+	case AGPT_LOBE_DIFFUSE:
+	case AGPT_LOBE_RETRO: return Cosine_Pdf(wo, wi);
+	case AGPT_LOBE_MICROFACET: return Microfacet_Pdf(m, wo, wi);
+	default: return 0;        // SpecularReflection::Pdf (reflection.h:30)
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// BSDF (reflection.h:83-201, reflection.cpp:6-11)
+// ---------------------------------------------------------------------------------------
+struct DBSDF {
+	float3 ng, ns, ss, ts;
+	const agpt_material* mat;
+};
+__device__ __forceinline__ float3 WorldToLocal(const DBSDF& b, float3 v) { return f3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+__device__ __forceinline__ float3 LocalToWorld(const DBSDF& b, float3 v) {
+	return f3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z,
+		b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
+		b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+__device__ __forceinline__ bool BSDF_IsPerfectlySpecular(const DBSDF& b) { return (b.mat->lobes & ~AGPT_LOBE_SPECULAR) == 0; }
+
+__device__ __noinline__ float3 BSDF_f(const DBSDF& b, float3 woW, float3 wiW, bool skipSpecular) {
+	float3 wi = WorldToLocal(b, wiW), wo = WorldToLocal(b, woW);
+	if (wo.z == 0) return f3(0.f);
+	bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+	float3 f = f3(0.f);
+	int lobes[4];
+	int n = LobeList(*b.mat, skipSpecular, lobes);
+	for (int i = 0; i < n; i++)
+		if (reflect) f += Lobe_f(*b.mat, lobes[i], wo, wi);
+	return f;
+}
+__device__ __noinline__ float BSDF_Pdf(const DBSDF& b, float3 woW, float3 wiW, bool skipSpecular) {
+	if (b.mat->lobes == 0) return 0.f;
+	float3 wo = WorldToLocal(b, woW), wi = WorldToLocal(b, wiW);
+	if (wo.z == 0) return 0.f;
+	float pdf = 0.f;
+	int lobes[4];
+	int n = LobeList(*b.mat, skipSpecular, lobes);
+	for (int i = 0; i < n; i++) pdf += Lobe_Pdf(*b.mat, lobes[i], wo, wi);
+	return n > 0 ? pdf / n : 0.f;
+}
+// *pdf is written only where upstream writes it (callers pre-set it like upstream's locals).
+__device__ __noinline__ float3 BSDF_Sample_f(const DBSDF& b, float3 woW, float3* wiW, float2 u, float* pdf,
+		bool skipSpecular, bool* sampledSpecular) {
+	int lobes[4];
+	int matching = LobeList(*b.mat, skipSpecular, lobes);
+	if (matching == 0) { *pdf = 0; return f3(0.f); }
+	int comp = min((int)floorf(u.x * matching), matching - 1);
+	int lobe = lobes[comp];
+	float2 uR = make_float2(smin(u.x * matching - comp, AGPT_ONE_MINUS_EPS), u.y);
+	float3 wi = f3(0.f), wo = WorldToLocal(b, woW);
+	if (wo.z == 0) return f3(0.f);
+	*pdf = 0;
+	bool specular = lobe == AGPT_LOBE_SPECULAR;
+	if (sampledSpecular) *sampledSpecular = specular;
+	float3 f = f3(0.f);
+	const agpt_material& m = *b.mat;
+	if (specular) {
+		wi = f3(-wo.x, -wo.y, wo.z);
+		*pdf = 1;
+		f = f3(1.f) * f3(m.mirror_r) / AbsCosTheta(wi);       // FresnelNoOp (microfacet.h:230-233)
+	}
+	else if (lobe == AGPT_LOBE_MICROFACET) {
+		// MicrofacetReflection::Sample_f (reflection.h:55-66): early returns leave *pdf = 0
+		float3 wh = TR_Sample_wh(m.alpha_x, m.alpha_y, wo, uR);
+		if (!(dot(wo, wh) < 0)) {
+			wi = Reflect(wo, wh);
+			if (SameHemisphere(wo, wi)) *pdf = TR_Pdf(m.alpha_x, m.alpha_y, wo, wh) / (4 * dot(wo, wh));
+		}
+	}
+	else {
+		// BxDF::Sample_f cosine sampling (reflection.h:8-15)
+		wi = CosineSampleHemisphere(uR);
+		if (wo.z < 0) wi.z *= -1;
+		*pdf = Cosine_Pdf(wo, wi);
+	}
+	if (*pdf == 0) return f3(0.f);
+	*wiW = LocalToWorld(b, wi);
+	if (!specular && matching > 1)
+		for (int i = 0; i < matching; i++)
+			if (lobes[i] != lobe) *pdf += Lobe_Pdf(m, lobes[i], wo, wi);
+	if (matching > 1) *pdf /= matching;
+	if (!specular) {
+		bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+		f = f3(0.f);
+		for (int i = 0; i < matching; i++)
+			if (reflect) f += Lobe_f(m, lobes[i], wo, wi);
+	}
+	return f;
+}
+
+// ---------------------------------------------------------------------------------------
+// SurfaceInteraction (intersectable.h:63-115) rebuilt once for the closest hit
+// ---------------------------------------------------------------------------------------
+struct DSurface {
+	float3 p, n;          // point, geometric normal (after Faceforward by SetShadingGeometry)
+	float3 sn;            // shading.n
+	float3 sdpdu;         // shading.dpdu (== the geometric dpdu the interaction was built with, :76,:87)
+};
+__device__ __forceinline__ void SurfaceInit(DSurface& s, float3 p, float3 dpdu, float3 dpdv) {
+	s.p = p;
+	s.n = normalize(cross(dpdu, dpdv));
+	s.sn = s.n;
+	s.sdpdu = dpdu;
+}
+__device__ __forceinline__ DBSDF MakeBSDF(const DSurface& s, const agpt_material* m) {   // reflection.cpp:6-11
+	DBSDF b;
+	b.ng = s.n; b.ns = s.sn;
+	b.ss = normalize(s.sdpdu);
+	b.ts = cross(b.ns, b.ss);
+	b.mat = m;
+	return b;
+}
+
+// Sphere hit -> interaction (intersectable.h:183-204); dpdu/dpdv are passed swapped upstream.
+__device__ __forceinline__ void SphereSurface(const agpt_sphere& sp, float3 O, float3 D, float root, DSurface& s) {
+	float3 p = O + root * D;
+	float3 pHit = p - f3(sp.center);
+	if (pHit.x == 0 && pHit.y == 0) pHit.x = AGPT_EPSILON * sp.r;
+	float theta = racos(rclamp(pHit.z / sp.r, -1.f, 1.f));
+	float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
+	float invZRadius = 1 / zRadius;
+	float cosPhi = pHit.x * invZRadius;
+	float sinPhi = pHit.y * invZRadius;
+	float3 dpdu = f3(-AGPT_TWOPI * pHit.y, AGPT_TWOPI * pHit.x, 0);
+	float3 dpdv = AGPT_PI * f3(pHit.z * cosPhi, pHit.z * sinPhi, -sp.r * rsin(theta));
+	SurfaceInit(s, p, dpdv, dpdu);
+}
+__device__ __forceinline__ void PlaneSurface(float3 O, float3 D, float t, DSurface& s) {   // intersectable.h:128-133
+	SurfaceInit(s, O + t * D, f3(0, 0, 1), f3(1, 0, 0));
+}
+// Triangle hit -> interaction + shading frame (trianglemesh.cpp:45-113, intersectable.h:80-89)
+__device__ __forceinline__ void TriangleSurface(const DMesh& mesh, int slot, float3 O, float3 D, float t, float b1, float b2, DSurface& s) {
+	float4 a = __ldg(mesh.tris + 3 * slot), b = __ldg(mesh.tris + 3 * slot + 1), c = __ldg(mesh.tris + 3 * slot + 2);
+	float3 v0 = f3(a.x, a.y, a.z), v1 = f3(b.x, b.y, b.z), v2 = f3(c.x, c.y, c.z);
+	float b0 = 1.f - b1 - b2;
+	float2 uv0 = make_float2(0, 0), uv1 = make_float2(1, 0), uv2 = make_float2(1, 1);
+	if (mesh.uvs) { uv0 = __ldg(mesh.uvs + 3 * slot); uv1 = __ldg(mesh.uvs + 3 * slot + 1); uv2 = __ldg(mesh.uvs + 3 * slot + 2); }
+	float3 dpdu, dpdv;
+	TriangleDerivatives(v0, v1, v2, uv0, uv1, uv2, dpdu, dpdv);
+	SurfaceInit(s, O + t * D, dpdu, dpdv);
+	if (mesh.normals) {
+		float4 na = __ldg(mesh.normals + 3 * slot), nb = __ldg(mesh.normals + 3 * slot + 1), nc = __ldg(mesh.normals + 3 * slot + 2);
+		float3 ns = f3(na.x, na.y, na.z) * b0 + f3(nb.x, nb.y, nb.z) * b1 + f3(nc.x, nc.y, nc.z) * b2;
+		if (sqrLength(ns) > 0.f) ns = normalize(ns);
+		else ns = s.n;
+		float3 ss = normalize(dpdu);
+		float3 ts = cross(ss, ns);
+		if (sqrLength(ts) > 0.f) { ts = normalize(ts); ss = cross(ts, ns); }
+		else CoordinateSystem(ns, &ss, &ts);
+		// SetShadingGeometry(ss, ts, true): shading.n from the shading tangents, geometric n
+		// flipped toward it; shading.dpdu keeps the geometric dpdu (quirk)
+		s.sn = normalize(cross(ss, ts));
+		s.n = Faceforward(s.n, s.sn);
+	}
+}
+
+// ---------------------------------------------------------------------------------------
+// Sphere light sampling (intersectable.h:230-317)
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void SphereSampleFrom(const agpt_sphere& sp, float3 refP, float2 u, float3* pOut, float3* nOut, float* pdf) {
+	float3 pCenter = f3(sp.center);
+	if (sqrLength(refP - pCenter) <= sp.r2) {
+		// uniform area sampling (:230-237) converted to solid angle (:245-256)
+		float3 pObj = pCenter + sp.r * RandomInSphereU(u);
+		float3 n = normalize(pObj);      // upstream normalises the world position (kept)
+		*pdf = 1 / (4.f * AGPT_PI * sp.r2);
+		float3 wi = pObj - refP;
+		if (sqrLength(wi) == 0) *pdf = 0;
+		else {
+			wi = normalize(wi);
+			*pdf *= sqrLength(refP - pObj) / absdot(n, -wi);
+		}
+		if (isinf(*pdf)) *pdf = 0;
+		*pOut = pObj; *nOut = n;
+		return;
+	}
+	float dc = length(refP - pCenter);
+	float invDc = 1 / dc;
+	float3 wc = (pCenter - refP) * invDc;
+	float3 wcX, wcY;
+	CoordinateSystem(wc, &wcX, &wcY);
+	float sinThetaMax = sp.r * invDc;
+	float sinThetaMax2 = sinThetaMax * sinThetaMax;
+	float invSinThetaMax = 1 / sinThetaMax;
+	float cosThetaMax = sqrtf(smax(0.f, 1 - sinThetaMax2));
+	float cosTheta = (cosThetaMax - 1) * u.x + 1;
+	float sinTheta2 = 1 - cosTheta * cosTheta;
+	if (sinThetaMax2 < 0.00068523f) {
+		sinTheta2 = sinThetaMax2 * u.x;
+		cosTheta = sqrtf(1 - sinTheta2);
+	}
+	float cosAlpha = sinTheta2 * invSinThetaMax + cosTheta * sqrtf(smax(0.f, 1.f - sinTheta2 * invSinThetaMax * invSinThetaMax));
+	float sinAlpha = sqrtf(smax(0.f, 1.f - cosAlpha * cosAlpha));
+	float phi = u.y * 2 * AGPT_PI;
+	float3 nWorld = SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc);
+	*pOut = pCenter + sp.r * f3(nWorld.x, nWorld.y, nWorld.z);
+	*nOut = nWorld;
+	*pdf = 1 / (2 * AGPT_PI * (1 - cosThetaMax));
+}
+__device__ __forceinline__ float SpherePdfFrom(const agpt_sphere& sp, float3 refP) {
+	float3 pCenter = f3(sp.center);
+	if (sqrLength(refP - pCenter) <= sp.r2) return 1 / (4 * AGPT_PI);
+	float sinThetaMax2 = sp.r2 / sqrLength(refP - pCenter);
+	float cosThetaMax = sqrtf(smax(0.f, 1 - sinThetaMax2));
+	return UniformConePdf(cosThetaMax);
+}
+
+__device__ __forceinline__ float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {   // integrator.h:33-36
+	float f = nf * fPdf, g = ng * gPdf;
+	return (f * f) / (f * f + g * g);
+}

@@ -1,0 +1,238 @@
+// agpt_device.cuh -- device-side scene tables, strict-fp math and ray/primitive tests.
+//
+// Every function states the reference lines it realises.  This translation unit is built
+// with --fmad=false: a*b+c stays FMUL+FADD, `/` and sqrtf are IEEE (correctly rounded), so
+// +,-,*,/,sqrt sequences written in the reference's operation order give the same bits as
+// the g++ -O2 oracle on x86 (SURVEY 7 "hard parts").  min/max follow the template's
+// re-definitions `a<b?a:b` / `a>b?a:b` (template/precomp.h:364-365) and std::min/std::max
+// where the reference calls those -- they differ in which operand a NaN selects.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#include "agpt.h"
+
+#define AGPT_PI      3.14159265358979323846264f
+#define AGPT_INVPI   0.31830988618379067153777f
+#define AGPT_INV2PI  0.15915494309189533576888f
+#define AGPT_TWOPI   6.28318530717958647692528f
+#define AGPT_EPSILON 0.0001f
+#define AGPT_ONE_MINUS_EPS 0x1.fffffep-1f
+
+struct DMesh {
+	const float4* nodes;     // 2 x float4 per BVHNode; nullptr for a plain TriangleMesh
+	const float4* tris;      // 3 x float4 per triangle, leaf order; tris[3j].w != 0 marks a triangle upstream rejects as degenerate
+	const int* ids;          // original triangle number per slot
+	const float4* normals;   // 3 x float4 per triangle or nullptr
+	const float2* uvs;       // 3 x float2 per triangle or nullptr
+	int n_nodes, n_tris;
+};
+
+struct DScene {
+	const agpt_prim* prims;
+	const agpt_sphere* spheres;
+	const agpt_plane* planes;
+	const DMesh* meshes;
+	const agpt_material* mats;
+	const agpt_light* lights;
+	int n_prims, n_lights;
+	int width, height;
+	agpt_camera cam;
+};
+
+// ---------------------------------------------------------------------------------------
+// float3 helpers in the reference's operation order (template/precomp.h:427-768)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float s) { return make_float3(s, s, s); }
+__device__ __forceinline__ float3 f3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+__device__ __forceinline__ void operator*=(float3& a, float3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; }
+__device__ __forceinline__ void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
+__device__ __forceinline__ void operator/=(float3& a, float s) { a.x /= s; a.y /= s; a.z /= s; }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float sqrLength(float3 v) { return dot(v, v); }
+__device__ __forceinline__ float length(float3 v) { return sqrtf(dot(v, v)); }
+__device__ __forceinline__ float absdot(float3 a, float3 b) { return fabsf(dot(a, b)); }
+// normalize = v * (1/sqrtf(dot)), precomp.h:366,735
+__device__ __forceinline__ float3 normalize(float3 v) { float inv = 1.0f / sqrtf(dot(v, v)); return v * inv; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+	return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ bool IsBlack(float3 v) { return v.x == 0 && v.y == 0 && v.z == 0; }
+__device__ __forceinline__ float3 Faceforward(float3 v, float3 v2) { return (dot(v, v2) < 0.f) ? -v : v; }   // precomp.h:712
+__device__ __forceinline__ float3 Lerp(float t, float3 a, float3 b) { return (1 - t) * a + t * b; }          // precomp.h:676
+__device__ __forceinline__ float3 Reflect(float3 wo, float3 n) { return -wo + 2.0f * dot(wo, n) * n; }        // precomp.h:762
+
+// template fminf/fmaxf (precomp.h:364-365) and clamp (precomp.h:678)
+__device__ __forceinline__ float rmin(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float rmax(float a, float b) { return a > b ? a : b; }
+__device__ __forceinline__ float rclamp(float f, float a, float b) { return rmax(a, rmin(f, b)); }
+// std::max / std::min as libstdc++ defines them
+__device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
+
+// sinf/cosf/acosf: evaluated in double and rounded once.  glibc's float versions are
+// (almost always) the correctly rounded result, CUDA's sinf/cosf are 1-2 ulp routines; going
+// through double makes the device value agree with the oracle except in rare double-rounding
+// cases, which keeps most secondary paths bit-identical.  Off the traversal path.
+// Kept out of line: the double-precision routines are large and are called from many sites.
+__device__ __noinline__ float rsin(float x) { return (float)sin((double)x); }
+__device__ __noinline__ float rcos(float x) { return (float)cos((double)x); }
+__device__ __noinline__ float racos(float x) { return (float)acos((double)x); }
+__device__ __noinline__ void rsincos(float x, float* s, float* c) {
+	double ds, dc;
+	sincos((double)x, &ds, &dc);
+	*s = (float)ds; *c = (float)dc;
+}
+
+// common.h:145-151
+__device__ __forceinline__ void CoordinateSystem(float3 v1, float3* v2, float3* v3) {
+	if (fabsf(v1.x) > fabsf(v1.y)) *v2 = f3(-v1.z, 0, v1.x) / sqrtf(v1.x * v1.x + v1.z * v1.z);
+	else *v2 = f3(0, v1.z, -v1.y) / sqrtf(v1.y * v1.y + v1.z * v1.z);
+	*v3 = cross(v1, *v2);
+}
+
+// ---------------------------------------------------------------------------------------
+// RNG: Marsaglia xorshift32 of the template (template/template.cpp:666-685) on a per-path
+// state; stream start = WangHash(WangHash((pixel+1)*17) + sample), 0 -> 1 (cl/tools.cl:1-2,
+// SURVEY 8a row 3).
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t WangHash(uint32_t s) {
+	s = (s ^ 61u) ^ (s >> 16);
+	s *= 9u;
+	s = s ^ (s >> 4);
+	s *= 0x27d4eb2du;
+	s = s ^ (s >> 15);
+	return s;
+}
+__host__ __device__ __forceinline__ uint32_t StreamSeed(uint32_t pixel, uint32_t sample) {
+	uint32_t s = WangHash(WangHash((pixel + 1u) * 17u) + sample);
+	return s ? s : 1u;
+}
+__device__ __forceinline__ float RandomFloat(uint32_t& s) {
+	s ^= s << 13;
+	s ^= s >> 17;
+	s ^= s << 5;
+	return __uint2float_rn(s) * 2.3283064365387e-10f;
+}
+
+// ---------------------------------------------------------------------------------------
+// Ray: O, D = normalize(d), t (camera.h:3-15)
+// ---------------------------------------------------------------------------------------
+struct DRay {
+	float3 O, D;
+	float t;
+};
+__device__ __forceinline__ DRay MakeRay(float3 o, float3 d, float t = FLT_MAX) {
+	DRay r;
+	r.O = o; r.D = normalize(d); r.t = t;
+	return r;
+}
+
+// Bounds::Intersect (bvhtrimesh.h:18-36).  The per-axis early-outs of the reference are
+// folded into one test after the third axis: tmin never decreases, tmax never increases and
+// rounding of tmax*1.00000024f is monotonic, so "some axis failed" == "the last axis fails".
+// NaNs from 0/0 are dropped by the select order exactly as upstream drops them.
+__device__ __forceinline__ bool BoundsIntersect(float3 bmin, float3 bmax, float3 O, float3 D, float rayT, float& tEntry) {
+	float tmin = 0.0f, tmax = rayT;
+	{
+		float a = (bmin.x - O.x) / D.x, b = (bmax.x - O.x) / D.x;
+		float t0 = rmin(a, b), t1 = rmax(a, b);
+		tmin = rmax(t0, tmin); tmax = rmin(t1, tmax);
+	}
+	{
+		float a = (bmin.y - O.y) / D.y, b = (bmax.y - O.y) / D.y;
+		float t0 = rmin(a, b), t1 = rmax(a, b);
+		tmin = rmax(t0, tmin); tmax = rmin(t1, tmax);
+	}
+	{
+		float a = (bmin.z - O.z) / D.z, b = (bmax.z - O.z) / D.z;
+		float t0 = rmin(a, b), t1 = rmax(a, b);
+		tmin = rmax(t0, tmin); tmax = rmin(t1, tmax);
+	}
+	tEntry = tmin;
+	return !((tmax * 1.00000024f) < tmin);
+}
+
+// Moller-Trumbore of TriangleMesh::TriangleIntersect(P) (trianglemesh.cpp:7-43,117-155):
+// no culling, no epsilon; reject det==0, b1<0||b1>1, b2<0||b1+b2>1, t<=0||t>=ray.t.
+__device__ __forceinline__ bool TriangleTest(float3 v0, float3 v1, float3 v2, float3 O, float3 D, float rayT,
+		float& tOut, float& b1Out, float& b2Out) {
+	float3 e1 = v1 - v0;
+	float3 e2 = v2 - v0;
+	float3 pvec = cross(D, e2);
+	float det = dot(e1, pvec);
+	if (det == 0.0f) return false;
+	float inv_det = 1.0f / det;
+	float3 tvec = O - v0;
+	float b1 = dot(tvec, pvec) * inv_det;
+	if (b1 < 0.0f || b1 > 1.0f) return false;
+	float3 qvec = cross(tvec, e1);
+	float b2 = dot(D, qvec) * inv_det;
+	if (b2 < 0.0f || b1 + b2 > 1.0f) return false;
+	float t = dot(e2, qvec) * inv_det;
+	if (t <= 0.0f || t >= rayT) return false;
+	tOut = t; b1Out = b1; b2Out = b2;
+	return true;
+}
+
+// Triangle partial derivatives (trianglemesh.cpp:59-80).  Returns false when upstream
+// declares the triangle degenerate and drops the hit (:74-77).
+__device__ __forceinline__ bool TriangleDerivatives(float3 v0, float3 v1, float3 v2, float2 uv0, float2 uv1, float2 uv2,
+		float3& dpdu, float3& dpdv) {
+	float2 duv02 = make_float2(uv0.x - uv2.x, uv0.y - uv2.y), duv12 = make_float2(uv1.x - uv2.x, uv1.y - uv2.y);
+	float3 dp02 = v0 - v2, dp12 = v1 - v2;
+	float determinant = duv02.x * duv12.y - duv02.y * duv12.x;
+	bool degenerateUV = (double)fabsf(determinant) < 1e-8;
+	dpdu = f3(0.f); dpdv = f3(0.f);   // upstream leaves them uninitialised here; only read when !degenerateUV
+	if (!degenerateUV) {
+		float invdet = 1 / determinant;
+		dpdu = (duv12.y * dp02 - duv02.y * dp12) * invdet;
+		dpdv = (-duv12.x * dp02 + duv02.x * dp12) * invdet;
+	}
+	if (degenerateUV || sqrLength(cross(dpdu, dpdv)) == 0) {
+		float3 ng = cross(v2 - v0, v1 - v0);
+		if (sqrLength(ng) == 0) return false;
+		CoordinateSystem(normalize(ng), &dpdu, &dpdv);
+	}
+	return true;
+}
+
+// Sphere::Intersect / IntersectP root selection (intersectable.h:164-181,207-226); assumes |D|=1.
+__device__ __forceinline__ bool SphereTest(const agpt_sphere& s, float3 O, float3 D, float rayT, float& tOut) {
+	float3 oc = O - f3(s.center);
+	float half_b = dot(oc, D);
+	float c = sqrLength(oc) - s.r2;
+	float discriminant = half_b * half_b - c;
+	if (discriminant < 0) return false;
+	float sqrtd = sqrtf(discriminant);
+	float root = -half_b - sqrtd;
+	if (root < 0 || rayT < root) {
+		root = -half_b + sqrtd;
+		if (root < 0 || rayT < root) return false;
+	}
+	tOut = root;
+	return true;
+}
+
+// Plane::Intersect / IntersectP (intersectable.h:123-150).
+__device__ __forceinline__ bool PlaneTest(const agpt_plane& p, float3 O, float3 D, float rayT, float& tOut) {
+	if (D.y == 0) return false;
+	float t = (p.o[1] - O.y) / D.y;
+	if (t <= 0 || t >= rayT) return false;
+	float3 P = O + t * D;
+	float u = (P.x - p.o[0]) / p.half_x;
+	float v = (P.z - p.o[2]) / p.half_z;
+	if (fabsf(u) <= 1 && fabsf(v) <= 1) { tOut = t; return true; }
+	return false;
+}

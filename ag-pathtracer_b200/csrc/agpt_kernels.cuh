@@ -1,0 +1,483 @@
+// agpt_kernels.cuh -- the wavefront: path generation, trace, shade, accumulate, resolve.
+//
+// One wave = { closest-hit trace of the path rays + MIS rays queued by the previous shade,
+// any-hit trace of its shadow rays, shade }.  Shade realises one iteration of the loop of
+// PathTracer::Li (integrator.h:132-188) per path: it first folds the next-event estimate
+// of the PREVIOUS vertex into L (its shadow / MIS rays have just been traced), then handles
+// the new hit: emission, termination, null-material skip-through, light sampling
+// (UniformSampleOneLight + EstimateDirect, integrator.h:38-105), BSDF sampling, Russian
+// roulette, and queues the rays of the next wave with warp-ballot compaction.
+// The per-path RNG state lives in HBM, so the draw order inside a path is the reference's
+// whatever the scheduling.
+#pragma once
+
+#include "agpt_bsdf.cuh"
+#include "agpt_trace.cuh"
+
+// path flag bits (PathState::flags)
+#define PF_SPECULAR      1u     // specularBounce (integrator.h:129,177)
+#define PF_NEE_SHADOW    2u     // a shadow ray of the previous vertex is in flight
+#define PF_NEE_MIS       4u     // a MIS ray of the previous vertex is in flight
+#define PF_NO_CONTINUE   8u     // path ended at the previous vertex; only its NEE is left to fold in
+#define PF_BOUNCE_SHIFT  8
+
+struct PathState {
+	float4* rayO;        // O.xyz, tmax
+	float4* rayD;        // D.xyz
+	float4* hitA;        // t, b1, b2, int_as_float(prim)
+	int* hitSlot;
+	float4* beta;        // throughput
+	float4* L;           // radiance so far
+	uint32_t* rng;
+	uint32_t* flags;
+	float4* neeLight;    // f*Li*weight/lightPdf of the light-sampling strategy (integrator.h:57)
+	float4* neeMis;      // f*Lemit*weight/scatteringPdf of the BSDF strategy (integrator.h:88); w = int_as_float(light index)
+	float4* neeBeta;     // beta at the vertex the estimate belongs to
+	float4* shO;         // shadow ray O.xyz, tmax
+	float4* shD;
+	float4* misO;        // MIS ray
+	float4* misD;
+	int* shadowOccluded;
+	int* misPrim;        // primitive hit by the MIS ray, -1 = none
+	float4* Lout;        // finished radiance per path slot
+};
+
+struct WaveQueues {
+	int* closest;        // entries path*2 + kind (0 = path ray, 1 = MIS ray)
+	int* shadow;         // entries path
+	int* active;         // paths that take part in the next shade
+	int* counts;         // [0] closest, [1] shadow, [2] active
+};
+
+struct RayCounters {     // device-side totals, see agpt_stats
+	unsigned long long rays_closest, rays_shadow, rays_mis, rays_skip;
+};
+
+// ---- warp-aggregated append (warp-ballot ray-queue compaction) ---------------------------
+// All 32 lanes must call.  Returns the slot for lanes with pred, one atomic per warp.
+__device__ __forceinline__ int WarpAppend(bool pred, int* counter) {
+	unsigned mask = __ballot_sync(0xffffffffu, pred);
+	int lane = threadIdx.x & 31;
+	int base = 0;
+	if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- path generation: myapp.cpp:165-167 + Camera::GetRay (camera.h:58-64) ----------------
+__device__ __forceinline__ DRay CameraRay(const DScene& sc, int x, int y, uint32_t& rng) {
+	// float2 p(x + RandomFloat(), y + RandomFloat()): g++ evaluates the arguments right to
+	// left, so the y jitter is drawn first (oracle probe agpt_ref_probe_draw_order).
+	float jy = RandomFloat(rng);
+	float jx = RandomFloat(rng);
+	float px = x + jx, py = y + jy;
+	float s = px / sc.width, t = py / sc.height;            // Accumulator::PixelToFilm (myapp.h:57-59)
+	const agpt_camera& c = sc.cam;
+	float3 rd = f3(0.f);
+	if (c.lens_radius > 0.f) {
+		// RandomInUnitDisk (common.h:65-71): rejection loop, y drawn before x each round
+		while (true) {
+			float ry = -1 + (1 - -1) * RandomFloat(rng);
+			float rx = -1 + (1 - -1) * RandomFloat(rng);
+			float3 p = f3(rx, ry, 0);
+			if (sqrLength(p) >= 1) continue;
+			rd = c.lens_radius * p;
+			break;
+		}
+	}
+	float3 offset = f3(c.u) * rd.x + f3(c.v) * rd.y;
+	float3 pixel = f3(c.lower_left_corner) + s * f3(c.horizontal) + t * f3(c.vertical);
+	return MakeRay(f3(c.origin) + offset, pixel - f3(c.origin) - offset);
+}
+
+struct GenParams {
+	int n;                 // paths to start
+	int first_sample, sample_stride;
+	const int* xs;         // optional explicit pixel list (li_pixels); nullptr = whole film
+	const int* ys;
+	const int* ss;
+	const float* rays7;    // optional explicit rays (li_rays); O, D, tmax
+	const uint32_t* seeds;
+};
+
+__global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQueues q, GenParams g) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= g.n) return;
+	DRay ray;
+	uint32_t rng;
+	if (g.rays7) {
+		const float* r = g.rays7 + 7 * (size_t)i;
+		ray = MakeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]), r[6]);
+		rng = g.seeds[i] ? g.seeds[i] : 1u;
+	}
+	else {
+		int x, y, sample;
+		if (g.xs) { x = g.xs[i]; y = g.ys[i]; sample = g.ss[i]; }
+		else {
+			int wh = sc.width * sc.height;
+			int pixel = i % wh;
+			x = pixel % sc.width; y = pixel / sc.width;
+			sample = g.first_sample + (i / wh) * g.sample_stride;
+		}
+		rng = StreamSeed((uint32_t)(y * sc.width + x), (uint32_t)sample);
+		ray = CameraRay(sc, x, y, rng);
+	}
+	ps.rayO[i] = make_float4(ray.O.x, ray.O.y, ray.O.z, ray.t);
+	ps.rayD[i] = make_float4(ray.D.x, ray.D.y, ray.D.z, 0.f);
+	ps.beta[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+	ps.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	ps.rng[i] = rng;
+	ps.flags[i] = 0u;
+	q.closest[i] = i * 2;
+	q.active[i] = i;
+}
+
+// ---- trace kernels ---------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+		unsigned long long* counters) {
+	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	TraceCounters cnt = { 0, 0, 0, 0 };
+	if (i < count) {
+		int e = queue[i];
+		int path = e >> 1, kind = e & 1;
+		float4 o = kind ? ps.misO[path] : ps.rayO[path];
+		float4 d = kind ? ps.misD[path] : ps.rayD[path];
+		HitRecord hit;
+		TraceScene<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
+		if (kind == 0) {
+			ps.hitA[path] = make_float4(hit.t, hit.b1, hit.b2, __int_as_float(hit.prim));
+			ps.hitSlot[path] = hit.slot;
+		}
+		else ps.misPrim[path] = hit.prim;
+	}
+	if (COUNT) FlushCounters(cnt, counters);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+		unsigned long long* counters) {
+	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	TraceCounters cnt = { 0, 0, 0, 0 };
+	if (i < count) {
+		int path = queue[i];
+		float4 o = ps.shO[path], d = ps.shD[path];
+		HitRecord hit;
+		bool occluded = TraceScene<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
+		ps.shadowOccluded[path] = occluded ? 1 : 0;
+	}
+	if (COUNT) FlushCounters(cnt, counters);
+}
+
+// Standalone rays (agpt_trace_rays / agpt_trace_primary): hit table out.
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+		int count, agpt_hit* out, unsigned long long* counters) {
+	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	TraceCounters cnt = { 0, 0, 0, 0 };
+	if (i < count) {
+		float4 o = rayO[i], d = rayD[i];
+		HitRecord hit;
+		bool found = TraceScene<ANY, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
+		agpt_hit h;
+		h.found = found ? 1u : 0u;
+		h.prim = (found && !ANY) ? hit.prim : -1;
+		h.tri = -1;
+		if (found && !ANY && hit.slot >= 0) h.tri = sc.meshes[sc.prims[hit.prim].payload].ids[hit.slot];
+		h.t = (found && !ANY) ? hit.t : 0.f;
+		out[i] = h;
+	}
+	if (COUNT) FlushCounters(cnt, counters);
+}
+
+// ---- shade -------------------------------------------------------------------------------
+struct ShadeParams {
+	int count;            // entries in q.active (this wave)
+	int max_depth;
+	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
+};
+
+__device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
+	// for (light : scene.lights) if (light->IsInfinite()) L += beta * light->Le(ray)  (integrator.h:144-145)
+	// handled by the caller per light to keep the add order
+	return f3(0.f);
+}
+
+__global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool valid = i < sp.count;
+	int path = valid ? qin.active[i] : 0;
+
+	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false;
+
+	if (valid) {
+		uint32_t flags = ps.flags[path];
+		float4 L4 = ps.L[path];
+		float3 L = f3(L4.x, L4.y, L4.z);
+		float4 b4 = ps.beta[path];
+		float3 beta = f3(b4.x, b4.y, b4.z);
+		const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
+
+		// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
+		if (flags & (PF_NEE_SHADOW | PF_NEE_MIS)) {
+			float3 Ld = f3(0.f);
+			if ((flags & PF_NEE_SHADOW) && !ps.shadowOccluded[path]) {
+				float4 t = ps.neeLight[path];
+				Ld += f3(t.x, t.y, t.z);
+			}
+			if (flags & PF_NEE_MIS) {
+				float4 t = ps.neeMis[path];
+				int lightIdx = __float_as_int(t.w);
+				int hitPrim = ps.misPrim[path];
+				bool lit;
+				if (hitPrim >= 0) lit = sc.prims[hitPrim].area_light == lightIdx;          // lightIsect.shape->GetAreaLight() == &light
+				else lit = sc.lights[lightIdx].type == AGPT_LIGHT_UNIFORM_INFINITE;      // light.Le(ray): only infinite lights emit
+				if (lit && !IsBlack(f3(sc.lights[lightIdx].lemit))) Ld += f3(t.x, t.y, t.z);
+			}
+			float4 nb = ps.neeBeta[path];
+			L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
+			flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
+		}
+
+		bool finished = false;
+		if (flags & PF_NO_CONTINUE) finished = true;
+		else {
+			// (2) the new vertex: ray and its closest hit
+			float4 o4 = ps.rayO[path], d4 = ps.rayD[path];
+			float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
+			float4 h = ps.hitA[path];
+			int hitPrim = __float_as_int(h.w);
+			bool found = hitPrim >= 0;
+			int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
+			bool specularBounce = flags & PF_SPECULAR;
+
+			// emitted light at the vertex or from the environment (integrator.h:139-147)
+			if (bounces == 0 || specularBounce) {
+				if (found) {
+					int al = sc.prims[hitPrim].area_light;
+					if (al >= 0) L += beta * f3(sc.lights[al].lemit);
+					else L += beta * f3(0.f);
+				}
+				else {
+					for (int l = 0; l < sc.n_lights; l++)
+						if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
+				}
+			}
+
+			if (!found || bounces >= sp.max_depth) finished = true;     // integrator.h:150
+			else {
+				agpt_prim prim = sc.prims[hitPrim];
+				// SurfaceInteraction of the closest hit
+				DSurface si;
+				if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
+				else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
+				else TriangleSurface(sc.meshes[prim.payload], ps.hitSlot[path], O, D, h.x, h.y, h.z, si);
+
+				if (prim.material < 0) {
+					// null material: pass straight through, bounce count unchanged (integrator.h:152-161)
+					DRay nr = MakeRay(si.p + AGPT_EPSILON * D, D);
+					ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
+					ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
+					emitExtend = true; skipRay = true; stayActive = true;
+				}
+				else {
+					const agpt_material* mat = sc.mats + prim.material;
+					DBSDF bsdf = MakeBSDF(si, mat);
+					float3 wo = -D;
+					uint32_t rng = ps.rng[path];
+
+					// (3) UniformSampleOneLight (integrator.h:95-105) unless perfectly specular (:165)
+					if (!BSDF_IsPerfectlySpecular(bsdf) && sc.n_lights > 0) {
+						int nLights = sc.n_lights;
+						int numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
+						float2 uLight, uScattering;
+						uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);            // right-to-left argument order
+						uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
+						const agpt_light& light = sc.lights[numLight];
+						float3 lemit = f3(light.lemit);
+
+						// EstimateDirect (integrator.h:38-93): light sampling strategy
+						float3 wi = f3(0.f);
+						float lightPdf = 0, scatteringPdf = 0;
+						float3 Li = f3(0.f);
+						DRay vis;
+						vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
+						if (light.type == AGPT_LIGHT_AREA) {
+							// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
+							const agpt_prim& lp = sc.prims[light.prim];
+							if (lp.type == AGPT_PRIM_SPHERE) {
+								float3 pS, nS;
+								SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
+								if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
+								else {
+									wi = pS - si.p;
+									float dist = length(wi);
+									wi /= dist;
+									vis = MakeRay(si.p + AGPT_EPSILON * wi, wi, dist - 10 * AGPT_EPSILON);
+									Li = lemit;
+								}
+							}
+						}
+						else {
+							// UniformInfiniteLight::Sample_Li (lights.cpp:15-24): ignores u, draws 2 more
+							float a = 1 - 2 * RandomFloat(rng);
+							float b = sqrtf(1 - a * a);
+							float phi = 2 * AGPT_PI * RandomFloat(rng);
+							float sphi, cphi;
+							rsincos(phi, &sphi, &cphi);
+							float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
+							if (dot(v, si.sn) < 0) v = -v;
+							wi = v;
+							lightPdf = AGPT_INV2PI;
+							vis = MakeRay(si.p + AGPT_EPSILON * wi, wi);
+							Li = lemit;
+						}
+						if (lightPdf > 0 && !IsBlack(Li)) {
+							float3 f = BSDF_f(bsdf, wo, wi, true) * absdot(wi, si.sn);
+							scatteringPdf = BSDF_Pdf(bsdf, wo, wi, true);
+							if (!IsBlack(f)) {
+								float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
+								float3 term = f * Li * weight / lightPdf;
+								ps.neeLight[path] = make_float4(term.x, term.y, term.z, 0.f);
+								ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
+								ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
+								emitShadow = true;
+							}
+						}
+						// BSDF sampling strategy with MIS (integrator.h:62-90)
+						{
+							float3 wim = f3(0.f);
+							float3 f = BSDF_Sample_f(bsdf, wo, &wim, uScattering, &scatteringPdf, true, nullptr);
+							f *= absdot(wim, si.sn);
+							if (!IsBlack(f) && scatteringPdf > 0) {
+								float lp;
+								if (light.type == AGPT_LIGHT_AREA) {
+									const agpt_prim& lpr = sc.prims[light.prim];
+									lp = lpr.type == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lpr.payload], si.p) : 0.f;
+								}
+								else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
+								if (lp != 0) {
+									float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
+									float3 term = f * lemit * weight / scatteringPdf;
+									DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
+									ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
+									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
+									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
+									emitMis = true;
+								}
+							}
+						}
+						if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+					}
+
+					// (4) sample the BSDF for the new direction (integrator.h:169-177)
+					float2 u;
+					u.y = RandomFloat(rng); u.x = RandomFloat(rng);
+					float3 wi = f3(0.f);
+					float pdf = 0.f;
+					bool sampledSpecular = false;
+					float3 f = BSDF_Sample_f(bsdf, wo, &wi, u, &pdf, false, &sampledSpecular);
+					bool alive = !(IsBlack(f) || pdf == 0);
+					if (alive) {
+						beta *= f * absdot(wi, si.sn) / pdf;
+						specularBounce = sampledSpecular;
+						// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
+						float maxComponent = smax(beta.x, smax(beta.y, beta.z));
+						if (maxComponent < 1 && sp.rr_depth_arg > 3) {
+							float q = smax(.05f, 1 - maxComponent);
+							if (RandomFloat(rng) < q) alive = false;
+							else beta /= 1 - q;
+						}
+					}
+					if (alive) {
+						bounces++;
+						// the vertex at bounces == max_depth only adds emission, and only after a
+						// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
+						if (bounces >= sp.max_depth && !specularBounce) alive = false;
+					}
+					if (alive) {
+						DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
+						ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
+						ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
+						ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+						emitExtend = true; stayActive = true;
+					}
+					else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
+					else finished = true;
+					ps.rng[path] = rng;
+					flags = (flags & 0xffu & ~PF_SPECULAR) | (specularBounce ? PF_SPECULAR : 0u) | ((uint32_t)bounces << PF_BOUNCE_SHIFT);
+					if (emitShadow) flags |= PF_NEE_SHADOW;
+					if (emitMis) flags |= PF_NEE_MIS;
+				}
+			}
+		}
+		ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
+		ps.flags[path] = flags;
+		if (finished) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);
+	}
+
+	// (5) queue the next wave: one atomic per warp per queue
+	int slot = WarpAppend(emitExtend, qout.counts + 0);
+	if (emitExtend) qout.closest[slot] = path * 2;
+	slot = WarpAppend(emitMis, qout.counts + 0);
+	if (emitMis) qout.closest[slot] = path * 2 + 1;
+	slot = WarpAppend(emitShadow, qout.counts + 1);
+	if (emitShadow) qout.shadow[slot] = path;
+	slot = WarpAppend(stayActive, qout.counts + 2);
+	if (stayActive) qout.active[slot] = path;
+
+	// ray statistics (warp-reduced)
+	unsigned m;
+	int lane = threadIdx.x & 31;
+	m = __ballot_sync(0xffffffffu, emitExtend); if (lane == 0 && m) atomicAdd(&rc->rays_closest, (unsigned long long)__popc(m));
+	m = __ballot_sync(0xffffffffu, emitMis);    if (lane == 0 && m) atomicAdd(&rc->rays_mis, (unsigned long long)__popc(m));
+	m = __ballot_sync(0xffffffffu, emitShadow); if (lane == 0 && m) atomicAdd(&rc->rays_shadow, (unsigned long long)__popc(m));
+	m = __ballot_sync(0xffffffffu, skipRay);    if (lane == 0 && m) atomicAdd(&rc->rays_skip, (unsigned long long)__popc(m));
+}
+
+// ---- accumulate: myapp.cpp:169-173 + Accumulator::AddSample (myapp.h:17-19) --------------
+// One thread per pixel adds its samples of this batch in ascending sample order, the order
+// the reference's successive Ticks add them in.
+__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ Lout, float4* accum, int width, int height, int samplesInBatch) {
+	int pixel = blockIdx.x * blockDim.x + threadIdx.x;
+	int wh = width * height;
+	if (pixel >= wh) return;
+	int x = pixel % width, y = pixel / width;
+	float4* dst = accum + (size_t)(height - 1 - y) * width + x;
+	float4 a = *dst;
+	for (int s = 0; s < samplesInBatch; s++) {
+		float4 c = Lout[(size_t)s * wh + pixel];
+		float lum = 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z;     // Luminance (precomp.h:717)
+		if (isnan(c.x) || isnan(c.y) || isnan(c.z) || isinf(lum)) c = make_float4(0.f, 0.f, 0.f, 0.f);
+		a.x += c.x; a.y += c.y; a.z += c.z;
+	}
+	*dst = a;
+}
+
+// ---- resolve: Accumulator::CopyToSurface (myapp.h:34-41) + lin2rgb / rgb2uint (common.h:41-51)
+__global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accum, uint32_t* out, int n, float samples) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 a = accum[i];
+	float e = 1 / 2.2f;
+	float3 c = f3(powf(a.x / samples, e), powf(a.y / samples, e), powf(a.z / samples, e));
+	// rgb2uint clamps in double: clamp(clr.x, 0.0, 0.999) (common.h:47)
+	auto ch = [](float v) { double d = (double)v; d = d < 0.999 ? d : 0.999; d = 0.0 > d ? 0.0 : d; return (int)(256 * d); };
+	int r = ch(c.x), g = ch(c.y), b = ch(c.z);
+	out[i] = (uint32_t)((r << 16) + (g << 8) + b);
+}
+
+// ---- upload-time pass: flag triangles upstream would reject as degenerate (trianglemesh.cpp:71-77)
+__global__ void k_flag_degenerate(float4* tris, const float2* uvs, int n) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	float4 a = tris[3 * j], b = tris[3 * j + 1], c = tris[3 * j + 2];
+	float2 uv0 = make_float2(0, 0), uv1 = make_float2(1, 0), uv2 = make_float2(1, 1);
+	if (uvs) { uv0 = uvs[3 * j]; uv1 = uvs[3 * j + 1]; uv2 = uvs[3 * j + 2]; }
+	float3 dpdu, dpdv;
+	bool ok = TriangleDerivatives(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), uv0, uv1, uv2, dpdu, dpdv);
+	tris[3 * j].w = ok ? 0.f : 1.f;
+}

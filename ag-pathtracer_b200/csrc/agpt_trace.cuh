@@ -1,0 +1,178 @@
+// agpt_trace.cuh -- Scene::Intersect / Scene::IntersectP on the device.
+//
+// Closest-hit: scene.h:5-13 -> per primitive in list order, BVHTriMesh::Intersect
+// (bvhtrimesh.h:185-191) -> RecursiveHit (:332-384) as an iterative, near-first walk with an
+// explicit stack.  Any-hit: scene.h:15-19 -> RecursiveHitP (:386-413), order-free, early out.
+//
+// Result equivalence with the recursion: the near child is descended first, the far child
+// is pushed iff both boxes were hit (swap iff rightDist < leftDist, :359-372) and is NOT
+// re-tested against the shrunken ray.t when popped (upstream does not either, :379) -- its
+// leaves' triangles are simply rejected by t >= ray.t.  Equal-t ties therefore go to the
+// triangle upstream visits first.
+//
+// Node fetch: a sibling pair is one 64-byte line = four 128-bit loads (north star item 1);
+// a leaf-ordered triangle is three 128-bit loads.
+#pragma once
+
+#include "agpt_device.cuh"
+
+#define AGPT_STACK_SMEM 24      // stack entries per thread kept in shared memory
+#define AGPT_STACK_LOCAL 40     // overflow entries in local memory (SAH trees here are <= ~30 deep)
+#define AGPT_TRACE_THREADS 128
+
+struct TraceCounters {
+	unsigned long long node_visits, box_tests, tri_tests, analytic_tests;
+};
+
+struct HitRecord {
+	float t;
+	float b1, b2;     // barycentrics of a triangle hit (trianglemesh.cpp:28,35)
+	int prim;         // index in Scene::primitives, -1 = miss
+	int slot;         // leaf-order triangle slot inside the mesh, -1 for sphere / plane
+};
+
+// Stack entry encoding: bit 31 set -> single-triangle leaf, low bits = triangle slot;
+// otherwise bit 30 set -> multi-triangle leaf, low bits = node index (re-read first/count);
+// otherwise interior node, value = index of its left child (the pair base).
+#define AGPT_ENT_LEAF1 0x80000000u
+#define AGPT_ENT_LEAFN 0x40000000u
+
+__device__ __forceinline__ unsigned EncodeNode(int nodeIndex, int first, int count) {
+	if (count == 0) return (unsigned)first;
+	if (count == 1) return AGPT_ENT_LEAF1 | (unsigned)first;
+	return AGPT_ENT_LEAFN | (unsigned)nodeIndex;
+}
+
+struct NodeBox {
+	float3 bmin, bmax;
+	int first, count;
+};
+__device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, int i) {
+	float4 a = __ldg(nodes + 2 * i), b = __ldg(nodes + 2 * i + 1);
+	NodeBox n;
+	n.bmin = f3(a.x, a.y, a.z);
+	n.bmax = f3(a.w, b.x, b.y);
+	n.first = __float_as_int(b.z);
+	n.count = __float_as_int(b.w);
+	return n;
+}
+
+// One mesh.  `stack` points at this thread's shared-memory column (stride = blockDim.x).
+// ANY: return true on the first accepted triangle.  Otherwise updates hit / rayT.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, float3 O, float3 D, float& rayT, HitRecord& hit,
+		unsigned* stack, int stackStride, TraceCounters& cnt) {
+	bool found = false;
+	if (mesh.nodes == nullptr) {
+		// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
+		for (int j = 0; j < mesh.n_tris; j++) {
+			float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
+			if (COUNT) cnt.tri_tests++;
+			float t, b1, b2;
+			if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+				if (ANY) return true;
+				rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
+				found = true;
+			}
+		}
+		return found;
+	}
+
+	unsigned local[AGPT_STACK_LOCAL];
+	NodeBox root = LoadNode(mesh.nodes, 0);
+	float dist;
+	if (COUNT) cnt.box_tests++;
+	if (!BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist)) return false;
+	unsigned cur = EncodeNode(0, root.first, root.count);
+	int sp = 0;
+	while (true) {
+		if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
+			// interior: fetch the sibling pair (64 B), test both boxes
+			NodeBox l = LoadNode(mesh.nodes, (int)cur), r = LoadNode(mesh.nodes, (int)cur + 1);
+			if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
+			float dl, dr;
+			bool hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
+			bool hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+			unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
+			if (hl && hr) {
+				// closest-hit: near first, far pushed; any-hit: left first (bvhtrimesh.h:400-411)
+				bool swapKids = ANY ? false : (dr < dl);
+				unsigned nearE = swapKids ? er : el, farE = swapKids ? el : er;
+				if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
+				sp++;
+				cur = nearE;
+				continue;
+			}
+			if (hl) { cur = el; continue; }
+			if (hr) { cur = er; continue; }
+		}
+		else {
+			int first, count;
+			if (cur & AGPT_ENT_LEAF1) { first = (int)(cur & 0x7fffffffu); count = 1; }
+			else {
+				NodeBox n = LoadNode(mesh.nodes, (int)(cur & 0x3fffffffu));
+				first = n.first; count = n.count;
+			}
+			for (int j = first; j < first + count; j++) {
+				float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
+				if (COUNT) cnt.tri_tests++;
+				float t, b1, b2;
+				if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+					if (ANY) return true;
+					rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
+					found = true;
+				}
+			}
+		}
+		if (sp == 0) break;
+		sp--;
+		cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
+	}
+	return found;
+}
+
+// Scene::Intersect (ANY=false) / Scene::IntersectP (ANY=true): primitives in list order.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D, float rayT, HitRecord& hit,
+		unsigned* stack, int stackStride, TraceCounters& cnt) {
+	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
+	bool found = false;
+	for (int p = 0; p < sc.n_prims; p++) {
+		agpt_prim prim = sc.prims[p];
+		if (prim.type == AGPT_PRIM_SPHERE) {
+			if (COUNT) cnt.analytic_tests++;
+			float t;
+			if (SphereTest(sc.spheres[prim.payload], O, D, rayT, t)) {
+				if (ANY) return true;
+				rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; found = true;
+			}
+		}
+		else if (prim.type == AGPT_PRIM_PLANE) {
+			if (COUNT) cnt.analytic_tests++;
+			float t;
+			if (PlaneTest(sc.planes[prim.payload], O, D, rayT, t)) {
+				if (ANY) return true;
+				rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; found = true;
+			}
+		}
+		else {
+			if (TraceMesh<ANY, COUNT>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt)) {
+				if (ANY) return true;
+				found = true;
+			}
+		}
+	}
+	return found;
+}
+
+// Warp-aggregated flush of per-thread counters: one atomic per counter per warp.
+__device__ __forceinline__ void FlushCounters(const TraceCounters& c, unsigned long long* global4) {
+	unsigned long long v[4] = { c.node_visits, c.box_tests, c.tri_tests, c.analytic_tests };
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		unsigned long long x = v[k];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+		if ((threadIdx.x & 31) == 0 && x) atomicAdd(global4 + k, x);
+	}
+}

@@ -1,0 +1,241 @@
+/* agpt.h -- C ABI of the B200-native path-tracing hot path (libagpt.so).
+ *
+ * The reference (voxel-tracer/ag-pathtracer) has no FFI or plugin layer: its hot path is
+ * entered per ray through `virtual float3 Integrator::Li(const Ray&, const Scene&, int depth)`
+ * (integrator.h:28-31) and per frame through the pixel loop of `MyApp::Tick`
+ * (myapp.cpp:163-175) storing through `Accumulator::AddSample` (myapp.h:17-19).  This header
+ * is the boundary the drop-in inserts there: host C++ (the reference's own classes, or the
+ * mirror in ag-pathtracer_b200/host/) flattens a Scene once and hands (scene, camera,
+ * sample range) to the device; the device hands an accumulator back.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative
+ * agpt_status, with a message in agpt_last_error(); no exceptions cross the boundary; one
+ * context per GPU; functions are thread-compatible per context (not thread-safe); all
+ * pointers are HOST pointers to caller-owned memory that may be freed when the call
+ * returns, unless the name says `_dev`.  There is no CPU fallback: without a usable CUDA
+ * device agpt_create() fails and nothing else can be called.
+ */
+#ifndef AGPT_H
+#define AGPT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agpt_ctx agpt_ctx;
+
+typedef enum agpt_status {
+	AGPT_OK = 0,
+	AGPT_ERR_INVALID = -1,   /* bad argument or inconsistent scene tables */
+	AGPT_ERR_CUDA = -2,      /* CUDA runtime error (message carries cudaGetErrorString) */
+	AGPT_ERR_STATE = -3,     /* call order: film / camera / scene not set yet */
+	AGPT_ERR_NOMEM = -4
+} agpt_status;
+
+/* ---- scene tables ------------------------------------------------------------------ */
+
+/* Verbatim BVHNode of the reference (bvhtrimesh.h:126-130): 32 bytes = 2 x 128-bit loads.
+ * count > 0: leaf, `first` = offset of its first triangle in the mesh's leaf-ordered
+ * triangle array; count == 0: interior, children at nodes[first] and nodes[first+1]
+ * (one 64-byte line, bvhtrimesh.h:175).  Root at 0, slot 1 unused. */
+typedef struct agpt_bvh_node {
+	float bmin[3];
+	float bmax[3];
+	int32_t first;
+	int32_t count;
+} agpt_bvh_node;
+
+/* One TriangleMesh / BVHTriMesh.  Triangles are LEAF-ORDERED: slot j holds the triangle
+ * that `primitives[j]` refers to in the reference (bvhtrimesh.h:339), so a leaf reads
+ * tri_verts[first .. first+count) directly instead of chasing
+ * primitives[].index -> indices[].vertex_index -> vertices[].
+ * n_nodes == 0: plain TriangleMesh, tested brute force in slot order with no bounds test
+ * (trianglemesh.h:25-35). */
+typedef struct agpt_mesh_desc {
+	const agpt_bvh_node* nodes;  /* n_nodes entries, or NULL */
+	int32_t n_nodes;
+	int32_t n_tris;
+	const float* tri_verts;      /* n_tris x 3 x float4: v0 v1 v2; .w unused */
+	const int32_t* tri_ids;      /* n_tris: original triangle number (indices[3*id..]) reported in agpt_hit.tri */
+	const float* tri_normals;    /* n_tris x 3 x float4 (n0 n1 n2) or NULL: mesh has no normals (trianglemesh.cpp:86) */
+	const float* tri_uvs;        /* n_tris x 3 x float2 or NULL: default uvs (0,0),(1,0),(1,1) (trianglemesh.cpp:52-56) */
+} agpt_mesh_desc;
+
+typedef struct agpt_sphere {     /* intersectable.h:159-162,319-321 */
+	float center[3];
+	float r;
+	float r2;                    /* radius*radius as the Sphere ctor rounds it */
+	float pad[3];
+} agpt_sphere;
+
+typedef struct agpt_plane {      /* intersectable.h:119-121,154-156: XZ plane through o, normal +y */
+	float o[3];
+	float half_x;
+	float half_z;
+	float pad[3];
+} agpt_plane;
+
+enum { AGPT_PRIM_SPHERE = 0, AGPT_PRIM_PLANE = 1, AGPT_PRIM_BVH_MESH = 2, AGPT_PRIM_MESH = 3 };
+
+/* Scene::primitives in list order (scene.h:5-13,27): order decides exact-t ties. */
+typedef struct agpt_prim {
+	int32_t type;        /* AGPT_PRIM_* */
+	int32_t payload;     /* index into the spheres / planes / meshes table of that type */
+	int32_t material;    /* index into materials, -1 = nullptr material (emissive shape, integrator.h:152-161) */
+	int32_t area_light;  /* index into lights of the AreaLight wrapping this shape, -1 = none */
+} agpt_prim;
+
+enum { AGPT_MAT_DISNEY = 1, AGPT_MAT_MIRROR = 2 };
+enum { AGPT_LOBE_DIFFUSE = 1, AGPT_LOBE_RETRO = 2, AGPT_LOBE_MICROFACET = 4, AGPT_LOBE_SPECULAR = 8 };
+
+/* Constants the reference's material constructors derive once (material.h:14-49,74-77). */
+typedef struct agpt_material {
+	int32_t type;         /* AGPT_MAT_* */
+	uint32_t lobes;       /* AGPT_LOBE_* in BSDF::bxdfs[] order: diffuse, retro, microfacet | specular */
+	float roughness;      /* DisneyRetro::roughness */
+	float metallic;       /* DisneyFresnel::metallic */
+	float diffuse_r[3];   /* (1-metallic)*color: R of DisneyDiffuse and DisneyRetro */
+	float eta;            /* 1.5 (material.h:65) */
+	float spec_r0[3];     /* DisneyFresnel::R0 = Lerp(metallic, SchlickR0FromEta(eta), color) */
+	float alpha_x;        /* max(.001, roughness^2) */
+	float mirror_r[3];    /* SpecularReflection::R */
+	float alpha_y;
+} agpt_material;
+
+enum { AGPT_LIGHT_AREA = 0, AGPT_LIGHT_UNIFORM_INFINITE = 1 };
+
+/* Scene::lights in list order (lights.h:37-51,72-87). */
+typedef struct agpt_light {
+	int32_t type;        /* AGPT_LIGHT_* */
+	int32_t prim;        /* AREA: scene primitive index of the emitting shape; else -1 */
+	float pad[2];
+	float lemit[3];
+	float pad2;
+} agpt_light;
+
+/* Derived camera vectors exactly as Camera::updateCoords leaves them (camera.h:77-90);
+ * computed on the host (tan, double->float), the device only adds and multiplies. */
+typedef struct agpt_camera {
+	float origin[3];
+	float lower_left_corner[3];
+	float horizontal[3];
+	float vertical[3];
+	float u[3];
+	float v[3];
+	float lens_radius;
+} agpt_camera;
+
+typedef struct agpt_hit {
+	uint32_t found;
+	int32_t prim;        /* index in Scene::primitives */
+	int32_t tri;         /* original triangle number inside that mesh, -1 for sphere / plane */
+	float t;
+} agpt_hit;
+
+typedef struct agpt_stats {
+	uint64_t paths;            /* camera paths started */
+	uint64_t rays_closest;     /* path rays through Scene::Intersect (integrator.h:136), skip-through rays included */
+	uint64_t rays_shadow;      /* any-hit visibility rays (integrator.h:50) */
+	uint64_t rays_mis;         /* closest-hit MIS rays (integrator.h:79) */
+	uint64_t rays_skip;        /* of rays_closest: continuation through null-material shapes (integrator.h:158) */
+	uint64_t node_visits;      /* interior sibling pairs fetched (64 B each); only with AGPT_FLAG_COUNTERS */
+	uint64_t box_tests;
+	uint64_t tri_tests;        /* 48 B each */
+	uint64_t analytic_tests;   /* sphere / plane records tested (32 B each) */
+	uint64_t kernel_launches;  /* launches of this library's kernels since agpt_reset_stats */
+	uint64_t waves;            /* wavefront iterations */
+	float ms_render;           /* device time of agpt_render calls (CUDA events on the context stream) */
+	float ms_trace;            /* share spent in the trace kernels */
+	float ms_shade;
+	float ms_other;
+} agpt_stats;
+
+/* agpt_render / agpt_trace_* flags */
+enum {
+	AGPT_FLAG_COUNTERS = 1u,      /* count node visits / box / triangle tests (slower kernels) */
+	AGPT_FLAG_TIMING = 2u,        /* bracket every kernel class with CUDA events (serialises) */
+	AGPT_FLAG_FAST_BOXES = 4u     /* result-identical reciprocal slab test instead of the strict one */
+};
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+
+int agpt_create(int device, agpt_ctx** out);                 /* fails loudly without CUDA */
+int agpt_destroy(agpt_ctx* ctx);
+const char* agpt_last_error(void);
+int agpt_device_count(int* out);
+/* Launch on the caller's CUDA stream (cudaStream_t as void*); NULL = the context's own. */
+int agpt_set_stream(agpt_ctx* ctx, void* cuda_stream);
+
+/* ---- scene upload (replaces the Scene the reference keeps in host memory, scene.h:27-29) */
+
+int agpt_upload_meshes(agpt_ctx* ctx, const agpt_mesh_desc* meshes, int n);
+int agpt_upload_spheres(agpt_ctx* ctx, const agpt_sphere* spheres, int n);
+int agpt_upload_planes(agpt_ctx* ctx, const agpt_plane* planes, int n);
+int agpt_upload_primitives(agpt_ctx* ctx, const agpt_prim* prims, int n);
+int agpt_upload_materials(agpt_ctx* ctx, const agpt_material* materials, int n);
+int agpt_upload_lights(agpt_ctx* ctx, const agpt_light* lights, int n);
+int agpt_set_camera(agpt_ctx* ctx, const agpt_camera* camera);          /* Camera, camera.h:38-56 */
+int agpt_set_film(agpt_ctx* ctx, int width, int height);                /* Accumulator(w,h), myapp.h:10-13 */
+int agpt_scene_bytes(agpt_ctx* ctx, uint64_t* out);                     /* resident scene bytes in HBM */
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* num_samples iterations of the MyApp::Tick pixel loop (myapp.cpp:163-175) for sample
+ * indices [first_sample, first_sample+num_samples) stepping by sample_stride (1 on one GPU,
+ * G when G GPUs split the samples s = g mod G), PathTracer(max_depth)::Li(ray, scene,
+ * rr_depth_arg) per pixel, accumulated into the device float4[W*H] accumulator. */
+int agpt_render(agpt_ctx* ctx, int first_sample, int num_samples, int sample_stride,
+		int max_depth, int rr_depth_arg, uint32_t flags);
+
+/* Hit table of the camera rays of one sample index: out_host[y*W + x] (parity gate). */
+int agpt_trace_primary(agpt_ctx* ctx, int sample, uint32_t flags, agpt_hit* out_host);
+
+/* Scene::Intersect (any_hit = 0) / Scene::IntersectP (any_hit != 0) for caller rays:
+ * rays7 = O.xyz, D.xyz (normalised like the Ray ctor, camera.h:7), tmax. */
+int agpt_trace_rays(agpt_ctx* ctx, int64_t n, const float* rays7, int any_hit, uint32_t flags, agpt_hit* out_host);
+
+/* Radiance of single camera paths without accumulation (Integrator::Li for the debug
+ * click, myapp.cpp:196-198): pixel (xs[i], ys[i]), sample ss[i] -> out_rgb[3*i..]. */
+int agpt_li_pixels(agpt_ctx* ctx, int n, const int* xs, const int* ys, const int* ss,
+		int max_depth, int rr_depth_arg, float* out_rgb);
+
+/* Integrator::Li(ray, scene, depth) for caller-supplied rays (integrator.h:28-31): rays7 as
+ * in agpt_trace_rays, rng_states[i] = xorshift32 state the path starts from (the reference
+ * draws from its one global generator instead). */
+int agpt_li_rays(agpt_ctx* ctx, int n, const float* rays7, const uint32_t* rng_states,
+		int max_depth, int rr_depth_arg, float* out_rgb);
+
+/* ---- accumulator (Accumulator, myapp.h:8-68) ----------------------------------------- */
+
+int agpt_clear(agpt_ctx* ctx);                                  /* Accumulator::Clear */
+int agpt_accum_ptr_dev(agpt_ctx* ctx, void** dev_ptr);          /* float4[W*H] in HBM, row (H-1-y): for NCCL */
+int agpt_set_accum_dev(agpt_ctx* ctx, void* dev_ptr);           /* accumulate into caller-owned device memory */
+int agpt_read_accum(agpt_ctx* ctx, float* host_rgba);           /* D2H of float4[W*H] */
+int agpt_write_accum(agpt_ctx* ctx, const float* host_rgba);    /* H2D (resume) */
+/* Accumulator::CopyToSurface (myapp.h:34-41): /samples, pow(1/2.2), 8-bit pack 0x00RRGGBB. */
+int agpt_resolve(agpt_ctx* ctx, int samples, uint32_t* host_rgb8);
+
+/* ---- observability ------------------------------------------------------------------- */
+
+int agpt_get_stats(agpt_ctx* ctx, agpt_stats* out);
+int agpt_reset_stats(agpt_ctx* ctx);
+
+/* ---- per-function probes (differential tests against single reference functions) ----- */
+
+/* Bounds::Intersect (bvhtrimesh.h:18-36): boxes6 = bmin,bmax; rays7 = O,D (as given),tmax. */
+int agpt_probe_bounds(agpt_ctx* ctx, int n, const float* boxes6, const float* rays7, int* out_hit, float* out_t);
+/* BSDF::f / Pdf / Sample_f on a frame built from (dpdu, dpdv) (reflection.h:114-188):
+ * in14 = dpdu3 dpdv3 wo3 wi3 u2; out12 = f3 pdf1 | sampled wi3 f3 pdf1 specular1. */
+int agpt_probe_bsdf(agpt_ctx* ctx, int n, const agpt_material* mat, const float* in14, int skip_specular, float* out12);
+/* Sphere::Sample(ref,u) / Sphere::Pdf (intersectable.h:239-317): in9 = center3 r refp3 u2;
+ * out8 = p3 n3 pdf pdf_only. */
+int agpt_probe_sphere_sample(agpt_ctx* ctx, int n, const float* in9, float* out8);
+/* First k floats of the RNG stream of (pixel_index, sample). */
+int agpt_probe_stream(agpt_ctx* ctx, uint32_t pixel_index, uint32_t sample, int k, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPT_H */

@@ -1,0 +1,62 @@
+/* agpt_host.h -- C ABI of libagpt_host.so: the host-side mirror of the reference's C++ API
+ * (ag-pathtracer_b200/host/) made reachable from C / Python (ctypes) for tests and bench.py.
+ *
+ * The mirror itself is C++ (Scene, Sphere, Plane, TriangleMesh, BVHTriMesh, Camera,
+ * DisneyMaterial, MirrorMaterial, AreaLight, UniformInfiniteLight, CudaPathTracer -- same
+ * names and constructor arguments as the headers under /root/reference); these entry points build the
+ * BASELINE.json configuration scenes through it (host/scenes/config_scenes.h, the same
+ * source the oracle compiles against the reference's own headers), flatten them into the
+ * tables of agpt.h, upload them, and render through CudaPathTracer::Render -- the call a
+ * user of the reference would make instead of looping MyApp::Tick (myapp.cpp:141-187).
+ * All compute goes through libagpt.so; nothing here traces or shades on the CPU.
+ */
+#ifndef AGPT_HOST_H
+#define AGPT_HOST_H
+
+#include "agpt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agpt_host_scene agpt_host_scene;
+typedef struct agpt_host_tracer agpt_host_tracer;
+
+const char* agpt_host_last_error(void);
+
+/* config 1..5 = BASELINE.json configs[0..4], 6 = test-only corner-case scene;
+ * level <= 0 picks the configuration's own icosphere subdivision level. */
+int agpt_host_scene_create(int config, int level, agpt_host_scene** out);
+int agpt_host_scene_destroy(agpt_host_scene* scene);
+/* film / integrator defaults of a configuration: out5 = width, height, spp, max_depth, depth_arg */
+int agpt_host_config_defaults(int config, int* out5, const char** name);
+/* counts4 = primitives, lights, triangles, BVH nodes; bytes = flattened scene size */
+int agpt_host_scene_counts(agpt_host_scene* scene, int64_t* counts4, uint64_t* bytes);
+/* Scene::Flatten() + agpt_upload_* + agpt_set_camera(Camera(scene.camera)) */
+int agpt_host_scene_upload(agpt_host_scene* scene, agpt_ctx* ctx);
+
+/* exports for comparison with the oracle's view of the same scene (oracle/ref_harness.cpp) */
+int agpt_host_camera_export(agpt_host_scene* scene, float* out19);
+int agpt_host_prim_info(agpt_host_scene* scene, int prim, int* kind, int* counts5, int* has_material, int* is_light);
+int agpt_host_bvh_export(agpt_host_scene* scene, int prim, void* nodes_out, int* leaf_tri_out);
+int agpt_host_mesh_export(agpt_host_scene* scene, int prim, float* tri_verts_out);
+int agpt_host_material_export(agpt_host_scene* scene, int prim, float* out20);
+/* DisneyMaterial(color, roughness, metallic) / MirrorMaterial(color) -> device record */
+int agpt_host_make_material(int type, const float* color3, float roughness, float metallic, agpt_material* out);
+
+/* CudaPathTracer(max_depth, device) */
+int agpt_host_tracer_create(int max_depth, int device, agpt_host_tracer** out);
+int agpt_host_tracer_destroy(agpt_host_tracer* tracer);
+int agpt_host_tracer_ctx(agpt_host_tracer* tracer, agpt_ctx** out);
+/* CudaPathTracer::Render(scene, Camera(scene.camera), Accumulator(width,height) over
+ * host_rgba, first_sample, num_samples, depth_arg): host buffers in, host buffers out.
+ * reupload != 0 forces a fresh Scene::Flatten + upload inside the call. */
+int agpt_host_tracer_render(agpt_host_tracer* tracer, agpt_host_scene* scene, int width, int height,
+		float* host_rgba, int first_sample, int num_samples, int depth_arg, uint32_t flags, int reupload);
+/* CudaPathTracer::Li(Ray(o, d), scene, depth_arg) */
+int agpt_host_tracer_li(agpt_host_tracer* tracer, agpt_host_scene* scene, const float* o3, const float* d3, int depth_arg, float* out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGPT_HOST_H */
