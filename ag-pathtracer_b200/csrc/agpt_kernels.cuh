@@ -139,13 +139,17 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc,
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	TraceCounters cnt = { 0, 0, 0, 0 };
-	if (i < count) {
-		int e = queue[i];
-		int path = e >> 1, kind = e & 1;
-		float4 o = kind ? ps.misO[path] : ps.rayO[path];
-		float4 d = kind ? ps.misD[path] : ps.rayD[path];
-		HitRecord hit;
-		TraceScene<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
+	bool lane = i < count;
+	int e = lane ? queue[i] : 0;
+	int path = e >> 1, kind = e & 1;
+	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
+	if (lane) {
+		o = kind ? ps.misO[path] : ps.rayO[path];
+		d = kind ? ps.misD[path] : ps.rayD[path];
+	}
+	HitRecord hit;
+	TraceScene<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	if (lane) {
 		if (kind == 0) {
 			ps.hitA[path] = make_float4(hit.t, hit.b1, hit.b2, __int_as_float(hit.prim));
 			ps.hitSlot[path] = hit.slot;
@@ -161,13 +165,13 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_any(DScene sc, Pat
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	TraceCounters cnt = { 0, 0, 0, 0 };
-	if (i < count) {
-		int path = queue[i];
-		float4 o = ps.shO[path], d = ps.shD[path];
-		HitRecord hit;
-		bool occluded = TraceScene<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
-		ps.shadowOccluded[path] = occluded ? 1 : 0;
-	}
+	bool lane = i < count;
+	int path = lane ? queue[i] : 0;
+	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
+	if (lane) { o = ps.shO[path]; d = ps.shD[path]; }
+	HitRecord hit;
+	bool occluded = TraceScene<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	if (lane) ps.shadowOccluded[path] = occluded ? 1 : 0;
 	if (COUNT) FlushCounters(cnt, counters);
 }
 
@@ -178,10 +182,12 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	TraceCounters cnt = { 0, 0, 0, 0 };
-	if (i < count) {
-		float4 o = rayO[i], d = rayD[i];
-		HitRecord hit;
-		bool found = TraceScene<ANY, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt);
+	bool lane = i < count;
+	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
+	if (lane) { o = rayO[i]; d = rayD[i]; }
+	HitRecord hit;
+	bool found = TraceScene<ANY, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	if (lane) {
 		agpt_hit h;
 		h.found = found ? 1u : 0u;
 		h.prim = (found && !ANY) ? hit.prim : -1;

@@ -58,20 +58,28 @@ __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, in
 }
 
 // One mesh.  `stack` points at this thread's shared-memory column (stride = blockDim.x).
-// ANY: return true on the first accepted triangle.  Otherwise updates hit / rayT.
+// ANY: stop at the first accepted triangle.  Otherwise updates hit / rayT.
+//
+// Convergence: the walk is a WARP-SYNCHRONOUS loop.  All 32 lanes stay in the loop until
+// every lane is done (`__any_sync` on the loop condition); a finished or invalid lane is
+// predicated off.  The loop has one back edge and every path through the body merges before
+// it, so the hardware re-converges the warp once per node step instead of letting lanes that
+// `continue`d early run ahead as separate fragments (measured: 2.3-3.1 of 32 threads active
+// per instruction with the naive while/continue form).  `lane` is false for threads past the
+// end of the queue; they must still call (full-mask votes).
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, float3 O, float3 D, float& rayT, HitRecord& hit,
-		unsigned* stack, int stackStride, TraceCounters& cnt) {
+		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	bool found = false;
 	if (mesh.nodes == nullptr) {
 		// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
 		for (int j = 0; j < mesh.n_tris; j++) {
 			float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
-			if (COUNT) cnt.tri_tests++;
 			float t, b1, b2;
-			if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
-				if (ANY) return true;
-				rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
+			bool test = lane && !(ANY && found);
+			if (COUNT && test) cnt.tri_tests++;
+			if (test && a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+				if (!ANY) { rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j; }
 				found = true;
 			}
 		}
@@ -81,85 +89,93 @@ __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, floa
 	unsigned local[AGPT_STACK_LOCAL];
 	NodeBox root = LoadNode(mesh.nodes, 0);
 	float dist;
-	if (COUNT) cnt.box_tests++;
-	if (!BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist)) return false;
+	if (COUNT && lane) cnt.box_tests++;
+	bool active = lane && BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist);
 	unsigned cur = EncodeNode(0, root.first, root.count);
 	int sp = 0;
-	while (true) {
-		if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
-			// interior: fetch the sibling pair (64 B), test both boxes
-			NodeBox l = LoadNode(mesh.nodes, (int)cur), r = LoadNode(mesh.nodes, (int)cur + 1);
-			if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
-			float dl, dr;
-			bool hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
-			bool hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
-			unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
-			if (hl && hr) {
-				// closest-hit: near first, far pushed; any-hit: left first (bvhtrimesh.h:400-411)
+	while (__any_sync(0xffffffffu, active)) {
+		if (active) {
+			bool pop = true;
+			if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
+				// interior: fetch the sibling pair (64 B), test both boxes
+				NodeBox l = LoadNode(mesh.nodes, (int)cur), r = LoadNode(mesh.nodes, (int)cur + 1);
+				if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
+				float dl, dr;
+				bool hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
+				bool hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+				unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
+				// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
+				// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
 				bool swapKids = ANY ? false : (dr < dl);
-				unsigned nearE = swapKids ? er : el, farE = swapKids ? el : er;
-				if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
-				sp++;
-				cur = nearE;
-				continue;
+				if (hl && hr) {
+					unsigned farE = swapKids ? el : er;
+					if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
+					sp++;
+					cur = swapKids ? er : el;
+					pop = false;
+				}
+				else if (hl || hr) { cur = hl ? el : er; pop = false; }
 			}
-			if (hl) { cur = el; continue; }
-			if (hr) { cur = er; continue; }
-		}
-		else {
-			int first, count;
-			if (cur & AGPT_ENT_LEAF1) { first = (int)(cur & 0x7fffffffu); count = 1; }
 			else {
-				NodeBox n = LoadNode(mesh.nodes, (int)(cur & 0x3fffffffu));
-				first = n.first; count = n.count;
+				int first, count;
+				if (cur & AGPT_ENT_LEAF1) { first = (int)(cur & 0x7fffffffu); count = 1; }
+				else {
+					NodeBox n = LoadNode(mesh.nodes, (int)(cur & 0x3fffffffu));
+					first = n.first; count = n.count;
+				}
+				for (int j = first; j < first + count; j++) {
+					float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
+					if (COUNT) cnt.tri_tests++;
+					float t, b1, b2;
+					if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+						found = true;
+						if (ANY) break;
+						rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
+					}
+				}
 			}
-			for (int j = first; j < first + count; j++) {
-				float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
-				if (COUNT) cnt.tri_tests++;
-				float t, b1, b2;
-				if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
-					if (ANY) return true;
-					rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
-					found = true;
+			if (ANY && found) active = false;
+			else if (pop) {
+				if (sp == 0) active = false;
+				else {
+					sp--;
+					cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
 				}
 			}
 		}
-		if (sp == 0) break;
-		sp--;
-		cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
 	}
 	return found;
 }
 
 // Scene::Intersect (ANY=false) / Scene::IntersectP (ANY=true): primitives in list order.
+// Every lane of the warp must call (lane=false for threads without a ray).
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D, float rayT, HitRecord& hit,
-		unsigned* stack, int stackStride, TraceCounters& cnt) {
+		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
 	bool found = false;
 	for (int p = 0; p < sc.n_prims; p++) {
 		agpt_prim prim = sc.prims[p];
+		bool test = lane && !(ANY && found);
+		if (ANY && !__any_sync(0xffffffffu, test)) break;     // warp-uniform early out of IntersectP
 		if (prim.type == AGPT_PRIM_SPHERE) {
-			if (COUNT) cnt.analytic_tests++;
+			if (COUNT && test) cnt.analytic_tests++;
 			float t;
-			if (SphereTest(sc.spheres[prim.payload], O, D, rayT, t)) {
-				if (ANY) return true;
-				rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; found = true;
+			if (test && SphereTest(sc.spheres[prim.payload], O, D, rayT, t)) {
+				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
+				found = true;
 			}
 		}
 		else if (prim.type == AGPT_PRIM_PLANE) {
-			if (COUNT) cnt.analytic_tests++;
+			if (COUNT && test) cnt.analytic_tests++;
 			float t;
-			if (PlaneTest(sc.planes[prim.payload], O, D, rayT, t)) {
-				if (ANY) return true;
-				rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; found = true;
+			if (test && PlaneTest(sc.planes[prim.payload], O, D, rayT, t)) {
+				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
+				found = true;
 			}
 		}
 		else {
-			if (TraceMesh<ANY, COUNT>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt)) {
-				if (ANY) return true;
-				found = true;
-			}
+			if (TraceMesh<ANY, COUNT>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
 		}
 	}
 	return found;
