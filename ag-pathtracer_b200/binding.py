@@ -35,16 +35,27 @@ class Material(ctypes.Structure):  # agpt_material
 
 
 class Stats(ctypes.Structure):  # agpt_stats
-    _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "node_visits",
-                                         "box_tests", "tri_tests", "analytic_tests", "kernel_launches", "waves")] + \
-               [(n, c_float) for n in ("ms_render", "ms_trace", "ms_shade", "ms_other")]
+    _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip")] + \
+               [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests")] + \
+               [(n, c_uint64) for n in ("kernel_launches", "launches_closest", "launches_any", "launches_shade", "waves")] + \
+               [(n, c_float) for n in ("ms_render", "ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other")]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {}
+        for n, t in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if hasattr(v, "__len__") else v
+        return d
 
     @property
     def rays(self):
         return self.rays_closest + self.rays_shadow + self.rays_mis
+
+    def algorithmic_bytes(self, k):
+        """64 B per interior visit + 48 B per triangle test + 32 B per analytic record
+        + 64 B per ray (ray in, hit out, queue traffic).  k = 0 closest-hit kernel, 1 any-hit kernel."""
+        rays = (self.rays_closest + self.rays_mis) if k == 0 else self.rays_shadow
+        return 64 * self.node_visits[k] + 48 * self.tri_tests[k] + 32 * self.analytic_tests[k] + 64 * rays
 
 
 HIT_DTYPE = np.dtype([("found", np.uint32), ("prim", np.int32), ("tri", np.int32), ("t", np.float32)])

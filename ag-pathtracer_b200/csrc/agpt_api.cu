@@ -76,7 +76,7 @@ struct agpt_ctx {
 	DevBuf<uint32_t> u32[2];
 	DevBuf<int> queues[6];        // closest A/B (2*cap), shadow A/B, active A/B
 	DevBuf<int> counts;           // 2 x 3
-	DevBuf<unsigned long long> traceCounters;   // 4
+	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned, 3 ints
 
@@ -171,7 +171,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	c->stream = c->ownStream;
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
-	CU(c->traceCounters.Alloc(4));
+	CU(c->traceCounters.Alloc(8));
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
 	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
@@ -356,40 +356,44 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		q[k].counts = c->counts.p + 3 * k;
 	}
 	int nClosest = n, nShadow = 0, nActive = n, cur = 0;
-	float msTrace = 0, msShade = 0;
+	float msClosest = 0, msAny = 0, msShade = 0;
+	unsigned long long* cntClosest = c->traceCounters.p;
+	unsigned long long* cntAny = c->traceCounters.p + 4;
 	while (nActive > 0) {
-		if (timing) CU(cudaEventRecord(c->evC, c->stream));
+		if (timing) CU(cudaEventRecord(c->evA, c->stream));
 		if (nClosest > 0) {
-			if (count) k_trace_closest<true><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, c->traceCounters.p);
-			else k_trace_closest<false><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, c->traceCounters.p);
-			c->stats.kernel_launches++;
+			if (count) k_trace_closest<true><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, cntClosest);
+			else k_trace_closest<false><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, cntClosest);
+			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
+		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (nShadow > 0) {
-			if (count) k_trace_any<true><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, c->traceCounters.p);
-			else k_trace_any<false><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, c->traceCounters.p);
-			c->stats.kernel_launches++;
+			if (count) k_trace_any<true><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, cntAny);
+			else k_trace_any<false><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, cntAny);
+			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
-		if (timing) CU(cudaEventRecord(c->evD, c->stream));
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
+		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = nActive; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
 		k_shade<<<Blocks(nActive, 128), 128, 0, c->stream>>>(sc, ps, q[cur], q[cur ^ 1], sp, c->rayCounters.p);
-		c->stats.kernel_launches++;
+		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
-		if (timing) CU(cudaEventRecord(c->evA, c->stream));
+		if (timing) CU(cudaEventRecord(c->evD, c->stream));
 		CU(cudaMemcpyAsync(c->hostCounts, q[cur ^ 1].counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 		if (timing) {
-			float a = 0, b = 0;
-			cudaEventElapsedTime(&a, c->evC, c->evD);
-			cudaEventElapsedTime(&b, c->evD, c->evA);
-			msTrace += a; msShade += b;
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, c->evA, c->evB);
+			cudaEventElapsedTime(&b, c->evB, c->evC);
+			cudaEventElapsedTime(&d, c->evC, c->evD);
+			msClosest += a; msAny += b; msShade += d;
 		}
 		nClosest = c->hostCounts[0]; nShadow = c->hostCounts[1]; nActive = c->hostCounts[2];
 		cur ^= 1;
 		c->stats.waves++;
 	}
-	c->stats.ms_trace += msTrace; c->stats.ms_shade += msShade;
+	c->stats.ms_trace_closest += msClosest; c->stats.ms_trace_any += msAny; c->stats.ms_shade += msShade;
 	return AGPT_OK;
 }
 
@@ -446,8 +450,8 @@ static int TraceTable(agpt_ctx* c, const DScene& sc, const float4* rayO, const f
 	const bool count = flags & AGPT_FLAG_COUNTERS;
 	int blocks = Blocks(n, AGPT_TRACE_THREADS);
 	if (any_hit) {
-		if (count) k_trace_table<true, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
-		else k_trace_table<true, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
+		if (count) k_trace_table<true, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
+		else k_trace_table<true, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
 	}
 	else {
 		if (count) k_trace_table<false, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
@@ -572,14 +576,16 @@ int agpt_get_stats(agpt_ctx* c, agpt_stats* out) {
 	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
-	unsigned long long tc[4];
+	unsigned long long tc[8];
 	RayCounters rc;
 	CU(cudaMemcpy(tc, c->traceCounters.p, sizeof(tc), cudaMemcpyDeviceToHost));
 	CU(cudaMemcpy(&rc, c->rayCounters.p, sizeof(rc), cudaMemcpyDeviceToHost));
 	*out = c->stats;
-	out->node_visits = tc[0]; out->box_tests = tc[1]; out->tri_tests = tc[2]; out->analytic_tests = tc[3];
+	for (int k = 0; k < 2; k++) {
+		out->node_visits[k] = tc[4 * k]; out->box_tests[k] = tc[4 * k + 1]; out->tri_tests[k] = tc[4 * k + 2]; out->analytic_tests[k] = tc[4 * k + 3];
+	}
 	out->rays_closest += rc.rays_closest; out->rays_shadow = rc.rays_shadow; out->rays_mis = rc.rays_mis; out->rays_skip = rc.rays_skip;
-	out->ms_other = out->ms_render - out->ms_trace - out->ms_shade;
+	out->ms_other = out->ms_render - out->ms_trace_closest - out->ms_trace_any - out->ms_shade;
 	return AGPT_OK;
 }
 int agpt_reset_stats(agpt_ctx* c) {

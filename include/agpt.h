@@ -140,16 +140,21 @@ typedef struct agpt_stats {
 	uint64_t rays_shadow;      /* any-hit visibility rays (integrator.h:50) */
 	uint64_t rays_mis;         /* closest-hit MIS rays (integrator.h:79) */
 	uint64_t rays_skip;        /* of rays_closest: continuation through null-material shapes (integrator.h:158) */
-	uint64_t node_visits;      /* interior sibling pairs fetched (64 B each); only with AGPT_FLAG_COUNTERS */
-	uint64_t box_tests;
-	uint64_t tri_tests;        /* 48 B each */
-	uint64_t analytic_tests;   /* sphere / plane records tested (32 B each) */
+	/* traversal work, only counted with AGPT_FLAG_COUNTERS; [0] closest-hit kernel, [1] any-hit kernel */
+	uint64_t node_visits[2];   /* interior sibling pairs fetched (64 B each) */
+	uint64_t box_tests[2];
+	uint64_t tri_tests[2];     /* triangles fetched and tested (48 B each) */
+	uint64_t analytic_tests[2];/* sphere / plane records tested (32 B each) */
 	uint64_t kernel_launches;  /* launches of this library's kernels since agpt_reset_stats */
+	uint64_t launches_closest; /* of which closest-hit trace, any-hit trace, shade */
+	uint64_t launches_any;
+	uint64_t launches_shade;
 	uint64_t waves;            /* wavefront iterations */
 	float ms_render;           /* device time of agpt_render calls (CUDA events on the context stream) */
-	float ms_trace;            /* share spent in the trace kernels */
+	float ms_trace_closest;    /* per kernel class, only with AGPT_FLAG_TIMING */
+	float ms_trace_any;
 	float ms_shade;
-	float ms_other;
+	float ms_other;            /* ms_render minus the three above (generate, accumulate, queue bookkeeping) */
 } agpt_stats;
 
 /* agpt_render / agpt_trace_* flags */

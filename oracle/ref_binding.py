@@ -58,6 +58,10 @@ class RefScene:
         except Exception:
             pass
 
+    def count_rays(self):
+        """Prepend the do-nothing ray-counting primitive (timing scenes only: shifts prim ids)."""
+        lib().agpt_ref_scene_count_rays(self._h)
+
     def counts(self):
         a, b = c_int(), c_int()
         lib().agpt_ref_scene_counts(self._h, byref(a), byref(b))
@@ -131,6 +135,12 @@ class RefScene:
         out = np.zeros(20, np.float32)
         lib().agpt_ref_material_export(self._h, c_int(prim), _fp(out))
         return out
+
+
+def ray_counts(reset=True):
+    out = (c_ulonglong * 2)()
+    lib().agpt_ref_ray_counts(out, c_int(1 if reset else 0))
+    return dict(closest=out[0], any=out[1])
 
 
 def probe_bounds(boxes6, rays7):

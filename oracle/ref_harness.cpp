@@ -99,13 +99,30 @@ bool MirrorSceneIntersect(const Scene& scene, const Ray& ray, SurfaceInteraction
 	return found;
 }
 
+// Ray counting without touching the reference: a do-nothing Intersectable put at the FRONT of
+// Scene::primitives is called exactly once per Scene::Intersect (scene.h:7-11) and once per
+// Scene::IntersectP (scene.h:16-18, before any early out); it never reports a hit, so results
+// are unchanged (primitive indices shift by one, so it is only used for timing runs).
+thread_local unsigned long long t_raysClosest = 0, t_raysAny = 0;
+std::atomic<unsigned long long> g_raysClosest(0), g_raysAny(0);
+class RayCounter : public Intersectable {
+public:
+	RayCounter() : Intersectable(nullptr) {}
+	bool Intersect(const Ray&, SurfaceInteraction&) const override { t_raysClosest++; return false; }
+	bool IntersectP(const Ray&) const override { t_raysAny++; return false; }
+};
+void FlushRayCounts() {
+	g_raysClosest += t_raysClosest; g_raysAny += t_raysAny;
+	t_raysClosest = t_raysAny = 0;
+}
+
 template <typename F>
 void ParallelRows(int y0, int y1, int threads, F&& body) {
-	if (threads <= 1) { for (int y = y0; y < y1; y++) body(y); return; }
+	if (threads <= 1) { for (int y = y0; y < y1; y++) body(y); FlushRayCounts(); return; }
 	std::atomic<int> next(y0);
 	std::vector<std::thread> pool;
 	for (int t = 0; t < threads; t++)
-		pool.emplace_back([&] { for (int y; (y = next.fetch_add(1)) < y1;) body(y); });
+		pool.emplace_back([&] { for (int y; (y = next.fetch_add(1)) < y1;) body(y); FlushRayCounts(); });
 	for (auto& t : pool) t.join();
 }
 
@@ -126,6 +143,17 @@ void* agpt_ref_scene_create(int config, int level) {
 }
 
 void agpt_ref_scene_destroy(void* h) { delete (RefScene*)h; }
+
+// Timing scenes only: prepend the ray counter (shifts primitive indices by one).
+void agpt_ref_scene_count_rays(void* h) {
+	auto* rs = (RefScene*)h;
+	rs->scene.primitives.insert(rs->scene.primitives.begin(), std::make_shared<RayCounter>());
+}
+// out2 = {Scene::Intersect calls, Scene::IntersectP calls} since the last reset.
+void agpt_ref_ray_counts(unsigned long long* out2, int reset) {
+	out2[0] = g_raysClosest; out2[1] = g_raysAny;
+	if (reset) { g_raysClosest = 0; g_raysAny = 0; }
+}
 
 int agpt_ref_scene_counts(void* h, int* n_prims, int* n_lights) {
 	auto* rs = (RefScene*)h;

@@ -21,10 +21,12 @@ def run(config, level, spp, flags=0, reps=2, W=None, H=None, depth=None):
         rays = s.rays
         out = dict(cfg=config, flags=f, ms=round(s.ms_render, 2), Mrays_s=round(rays / s.ms_render / 1e3, 1), Mpaths_s=round(s.paths / s.ms_render / 1e3, 1),
                    rays_per_path=round(rays / s.paths, 2), closest=s.rays_closest, shadow=s.rays_shadow, mis=s.rays_mis, waves=s.waves, launches=s.kernel_launches,
-                   ms_trace=round(s.ms_trace, 2), ms_shade=round(s.ms_shade, 2))
+                   ms_closest=round(s.ms_trace_closest, 2), ms_any=round(s.ms_trace_any, 2), ms_shade=round(s.ms_shade, 2))
         if f & agpt.FLAG_COUNTERS:
-            out.update(node_visits_per_ray=round(s.node_visits / rays, 2), tri_per_ray=round(s.tri_tests / rays, 2), analytic_per_ray=round(s.analytic_tests / rays, 2),
-                       bytes_per_ray=round((64 * s.node_visits + 48 * s.tri_tests + 32 * s.analytic_tests) / rays + 64, 1))
+            rc = s.rays_closest + s.rays_mis
+            out.update(closest_visits_per_ray=round(s.node_visits[0] / rc, 2), closest_tri_per_ray=round(s.tri_tests[0] / rc, 2),
+                       closest_analytic_per_ray=round(s.analytic_tests[0] / rc, 2), closest_bytes_per_ray=round(s.algorithmic_bytes(0) / rc, 1),
+                       any_visits_per_ray=round(s.node_visits[1] / max(s.rays_shadow, 1), 2), any_bytes_per_ray=round(s.algorithmic_bytes(1) / max(s.rays_shadow, 1), 1))
         print(json.dumps(out), flush=True)
     print(f"build {tb:.2f}s upload {tu:.2f}s scene {ctx.scene_bytes()/1e6:.1f} MB", flush=True)
     ctx.close()
