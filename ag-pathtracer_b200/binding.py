@@ -291,6 +291,12 @@ class HostScene:
         _check(host().agpt_host_camera_export(self._h, _fptr(out)), host_side=True)
         return out
 
+    def tables(self):
+        """agpt_scene_tables view (opaque bytes) of the flattened scene, valid while the scene lives."""
+        buf = ctypes.create_string_buffer(6 * 16 + 19 * 4 + 4)
+        _check(host().agpt_host_scene_tables(self._h, buf), host_side=True)
+        return buf
+
     def prim_info(self, prim):
         kind = c_int(); counts = (c_int * 5)(); hm = c_int(); il = c_int()
         _check(host().agpt_host_prim_info(self._h, c_int(prim), byref(kind), counts, byref(hm), byref(il)), host_side=True)

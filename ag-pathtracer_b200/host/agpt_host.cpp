@@ -91,6 +91,21 @@ int agpt_host_scene_upload(agpt_host_scene* s, agpt_ctx* ctx) {
 	HOST_TRY( return UploadFlat(Flat(s), *s->camera, ctx); )
 }
 
+int agpt_host_scene_tables(agpt_host_scene* s, agpt_scene_tables* out) {
+	if (!s || !out) return HostFail("null argument");
+	HOST_TRY(
+		FlatScene& f = Flat(s);
+		out->prims = f.prims.data(); out->n_prims = (int)f.prims.size();
+		out->spheres = f.spheres.data(); out->n_spheres = (int)f.spheres.size();
+		out->planes = f.planes.data(); out->n_planes = (int)f.planes.size();
+		out->meshes = f.meshes.data(); out->n_meshes = (int)f.meshes.size();
+		out->materials = f.materials.data(); out->n_materials = (int)f.materials.size();
+		out->lights = f.lights.data(); out->n_lights = (int)f.lights.size();
+		out->camera = s->camera->Export();
+	)
+	return AGPT_OK;
+}
+
 int agpt_host_camera_export(agpt_host_scene* s, float* out19) {
 	agpt_camera c = s->camera->Export();
 	memcpy(out19, &c, 19 * sizeof(float));

@@ -24,7 +24,6 @@ struct FlatScene {
 	std::vector<agpt_material> materials;
 	std::vector<agpt_light> lights;
 	std::vector<agpt_mesh_desc> meshes;
-	std::vector<std::vector<BVHNode>> meshNodes;   // copies are avoided: see Flatten()
 	std::vector<FlatTriangles> meshTris;
 	uint64_t Bytes() const {
 		uint64_t b = prims.size() * sizeof(agpt_prim) + spheres.size() * sizeof(agpt_sphere) + planes.size() * sizeof(agpt_plane)
@@ -49,7 +48,6 @@ public:
 		std::map<const Intersectable*, int> primIndex;
 		for (size_t i = 0; i < lights.size(); i++) lightIndex[lights[i].get()] = (int)i;
 		flat->meshTris.reserve(primitives.size());
-		flat->meshNodes.reserve(primitives.size());
 		for (size_t i = 0; i < primitives.size(); i++) {
 			const Intersectable* shape = primitives[i].get();
 			primIndex[shape] = (int)i;

@@ -235,7 +235,7 @@ def main():
 
     # samples are split by index across ranks: rank g renders s = g (mod world)
     def step(k, flags=0):
-        ctx.render(rank + k * spp_step * world, spp_step, depth, depth_arg, flags, sample_stride=world)
+        pkg.multigpu.render_sharded(ctx, k * spp_step * world, spp_step * world, depth, depth_arg, rank, world, flags)
 
     for k in range(args.warmup):
         step(k)
@@ -250,7 +250,7 @@ def main():
     for k in range(args.steps):
         step(args.warmup + k)
     if world > 1:
-        dist.all_reduce(accum, op=dist.ReduceOp.SUM)      # float4[W*H] accumulators -> final framebuffer (NVLink)
+        pkg.multigpu.allreduce_accumulator(accum)         # float4[W*H] accumulators -> final framebuffer (NVLink)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

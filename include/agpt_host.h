@@ -35,6 +35,19 @@ int agpt_host_scene_counts(agpt_host_scene* scene, int64_t* counts4, uint64_t* b
 /* Scene::Flatten() + agpt_upload_* + agpt_set_camera(Camera(scene.camera)) */
 int agpt_host_scene_upload(agpt_host_scene* scene, agpt_ctx* ctx);
 
+/* Borrowed view of the flattened tables (valid while the scene lives): what
+ * agpt_host_scene_upload hands to agpt_upload_*; tests feed the same tables to the CPU oracle. */
+typedef struct agpt_scene_tables {
+	const agpt_prim* prims; int n_prims;
+	const agpt_sphere* spheres; int n_spheres;
+	const agpt_plane* planes; int n_planes;
+	const agpt_mesh_desc* meshes; int n_meshes;
+	const agpt_material* materials; int n_materials;
+	const agpt_light* lights; int n_lights;
+	agpt_camera camera;
+} agpt_scene_tables;
+int agpt_host_scene_tables(agpt_host_scene* scene, agpt_scene_tables* out);
+
 /* exports for comparison with the oracle's view of the same scene (oracle/ref_harness.cpp) */
 int agpt_host_camera_export(agpt_host_scene* scene, float* out19);
 int agpt_host_prim_info(agpt_host_scene* scene, int prim, int* kind, int* counts5, int* has_material, int* is_light);

@@ -1,0 +1,75 @@
+"""GPU: BASELINE.json full sizes.  The CPU oracle cannot render 1080p x 256 spp in test time,
+so full-size checks are (a) the complete primary-hit table of one sample against the
+reference (2 M rays: seconds on the host cores) and (b) size-independent properties:
+determinism, additivity over sample ranges, sample-split equivalence, finite output."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def ctx2(agpt):
+    ctx = agpt.Context(0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg", [2, 3])
+def test_full_size_primary_hits_bit_exact(agpt, ref, ctx2, cfg):
+    """1080p, 1.31 M triangles: hit flag, primitive id, triangle id and t bits of every pixel."""
+    d = agpt.config_defaults(cfg)
+    W, H = d["width"], d["height"]
+    hs = agpt.HostScene(cfg, 0); rs = ref.RefScene(cfg, 0)
+    assert hs.counts()["tris"] >= 1310720
+    hs.upload(ctx2); ctx2.set_film(W, H)
+    want, st = rs.primary_hits(W, H, 0)
+    assert st["walk_mismatches"] == 0
+    ctx2.reset_stats()
+    got = ctx2.trace_primary(0, agpt.FLAG_COUNTERS)
+    for f in ("found", "prim", "tri"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(bits(got["t"]), bits(want["t"]))
+    s = ctx2.stats()
+    assert (s.node_visits[0], s.box_tests[0], s.tri_tests[0]) == (st["interior"], st["boxes"], st["tris"])
+
+
+def test_full_size_properties(agpt, ctx2):
+    cfg = 3
+    d = agpt.config_defaults(cfg)
+    W, H, md, da = d["width"], d["height"], d["max_depth"], d["depth_arg"]
+    hs = agpt.HostScene(cfg, 0)
+    hs.upload(ctx2); ctx2.set_film(W, H)
+    ctx2.clear(); ctx2.render(0, 4, md, da); a = ctx2.read_accum()
+    ctx2.clear(); ctx2.render(0, 4, md, da); b = ctx2.read_accum()
+    assert np.array_equal(bits(a), bits(b)), "run-to-run determinism"
+    ctx2.clear(); ctx2.render(0, 1, md, da); ctx2.render(1, 3, md, da); c = ctx2.read_accum()
+    assert np.array_equal(bits(a), bits(c)), "render(0..4) == render(0..1) then render(1..4)"
+    # sample split s = g (mod 2) as two GPUs would do it, summed: only fp32 order differs
+    ctx2.clear(); ctx2.render(0, 2, md, da, sample_stride=2); e = ctx2.read_accum()
+    ctx2.clear(); ctx2.render(1, 2, md, da, sample_stride=2); o = ctx2.read_accum()
+    denom = np.maximum(np.abs(a), 1e-3)
+    assert np.max(np.abs((e + o) - a) / denom) <= 1e-5
+    assert np.isfinite(a).all() and a[..., :3].min() >= 0
+
+
+def test_full_size_radiance_crop_vs_reference(agpt, ref, ctx2):
+    """A centred 256x144 crop of the full 1080p cfg-3 frame, 8 bounces, 4 spp, same streams."""
+    cfg = 3
+    d = agpt.config_defaults(cfg)
+    W, H, md, da, spp = d["width"], d["height"], d["max_depth"], d["depth_arg"], 4
+    hs = agpt.HostScene(cfg, 0); rs = ref.RefScene(cfg, 0)
+    hs.upload(ctx2); ctx2.set_film(W, H); ctx2.clear()
+    ctx2.render(0, spp, md, da)
+    got = ctx2.read_accum()
+    x0, y0, x1, y1 = (W - 256) // 2, (H - 144) // 2, (W + 256) // 2, (H + 144) // 2
+    want, _ = rs.render(W, H, 0, spp, md, da, crop=(x0, y0, x1, y1))
+    gv = got[::-1][y0:y1, x0:x1, :3].astype(np.float64); wv = want[::-1][y0:y1, x0:x1, :3].astype(np.float64)
+    err = float(np.sqrt(np.mean((gv - wv) ** 2)) / np.mean(np.abs(wv)))
+    exact = np.mean(np.all(gv == wv, axis=-1))
+    print(f"full-size crop: rel-RMSE {err:.3e}, bit-identical pixels {exact:.4f}")
+    assert err <= 1e-3
