@@ -81,18 +81,89 @@ __device__ __forceinline__ float rclamp(float f, float a, float b) { return rmax
 __device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
 __device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
 
-// sinf/cosf/acosf: evaluated in double and rounded once.  glibc's float versions are
-// (almost always) the correctly rounded result, CUDA's sinf/cosf are 1-2 ulp routines; going
-// through double makes the device value agree with the oracle except in rare double-rounding
-// cases, which keeps most secondary paths bit-identical.  Off the traversal path.
-// Kept out of line: the double-precision routines are large and are called from many sites.
-__device__ __noinline__ float rsin(float x) { return (float)sin((double)x); }
-__device__ __noinline__ float rcos(float x) { return (float)cos((double)x); }
-__device__ __noinline__ float racos(float x) { return (float)acos((double)x); }
-__device__ __noinline__ void rsincos(float x, float* s, float* c) {
-	double ds, dc;
-	sincos((double)x, &ds, &dc);
-	*s = (float)ds; *c = (float)dc;
+// sinf / cosf / acosf with the oracle's bits.  The reference calls libm; CUDA's sinf/cosf/
+// acosf are different 1-2 ulp routines, and even a correctly rounded result differs from
+// glibc's in ~0.8 % (sin/cos) and ~7.7 % (acos) of calls -- each such ulp is then amplified by
+// every later bounce off a curved surface.  So the device evaluates the SAME published
+// algorithms glibc 2.39 uses (the oracle's libm), which makes secondary rays bit-identical too:
+//   * sinf/cosf: ARM optimized-routines "sincosf" (glibc sysdeps/ieee754/flt-32/s_sinf.c,
+//     s_cosf.c, sincosf.h): reduction by pi/2 and odd/even minimax polynomials, all in double;
+//   * acosf: Sun fdlibm e_acosf.c rational approximation in float (glibc e_acosf.c).
+// Checked on the host against libm: 0 mismatches in 4e7 (sin, cos) and 2e7 (acos) arguments.
+// Arguments on this path lie in [-pi/4, 2 pi]; beyond |x| >= 120 (never reached) the slow
+// reduction is replaced by the double routine.  Kept out of line (called from many sites).
+__device__ __forceinline__ float SinCosPoly(double x, double x2, bool negate, int n) {
+	const double sg = negate ? -1.0 : 1.0;     // glibc's __sincosf_table[1] is table[0] with the cosine coefficients negated
+	if ((n & 1) == 0) {
+		double x3 = x * x2;
+		double s1 = 0x1.1107605230bc4p-7 + x2 * -0x1.994eb3774cf24p-13;
+		double x7 = x3 * x2;
+		double s = x + x3 * -0x1.555545995a603p-3;
+		return (float)(s + x7 * s1);
+	}
+	double x4 = x2 * x2;
+	double c2 = sg * -0x1.6c087e89a359dp-10 + x2 * (sg * 0x1.99343027bf8c3p-16);
+	double c1 = sg * -0x1.ffffffd0c621cp-2 + x2 * (sg * 0x1.55553e1068f19p-5);
+	double x6 = x4 * x2;
+	double c = sg * 0x1p0 + x2 * c1;
+	return (float)(c + x6 * c2);
+}
+__device__ __forceinline__ uint32_t AbsTop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
+// returns sin (cosine == false) or cos (cosine == true) of y
+__device__ __forceinline__ float GlibcSinCos(float y, bool cosine) {
+	double x = (double)y;
+	if (AbsTop12(y) < AbsTop12(0x1.921FB6p-1f)) {             // |y| < pi/4
+		double x2 = x * x;
+		if (AbsTop12(y) < AbsTop12(0x1p-12f)) return cosine ? 1.0f : y;
+		return SinCosPoly(x, x2, false, cosine ? 1 : 0);
+	}
+	if (AbsTop12(y) < AbsTop12(120.0f)) {
+		double r = x * 0x1.45F306DC9C883p+23;                 // 2/pi * 2^24
+		int n = (__double2int_rz(r) + 0x800000) >> 24;
+		x = x - n * 0x1.921FB54442D18p0;
+		double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;   // sign[4] = { 1, -1, -1, 1 }
+		return SinCosPoly(x * sgn, x * x, (n & 2) != 0, cosine ? (n ^ 1) : n);
+	}
+	return cosine ? (float)cos(x) : (float)sin(x);
+}
+__device__ __noinline__ float rsin(float x) { return GlibcSinCos(x, false); }
+__device__ __noinline__ float rcos(float x) { return GlibcSinCos(x, true); }
+__device__ __noinline__ void rsincos(float x, float* s, float* c) { *s = GlibcSinCos(x, false); *c = GlibcSinCos(x, true); }
+__device__ __noinline__ float racos(float x) {
+	const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f,
+		pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,
+		pS4 = 7.9153501429e-04f, pS5 = 3.4793309169e-05f,
+		qS1 = -2.4033949375e+00f, qS2 = 2.0209457874e+00f, qS3 = -6.8828397989e-01f, qS4 = 7.7038154006e-02f;
+	float z, p, q, r, w, s, c, df;
+	int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+	if (ix == 0x3f800000) return hx > 0 ? 0.0f : pi + 2.0f * pio2_lo;
+	if (ix > 0x3f800000) return (x - x) / (x - x);
+	if (ix < 0x3f000000) {                                    // |x| < 0.5
+		if (ix <= 0x23000000) return pio2_hi + pio2_lo;
+		z = x * x;
+		p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+		q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+		r = p / q;
+		return pio2_hi - (x - (pio2_lo - x * r));
+	}
+	if (hx < 0) {                                             // x < -0.5
+		z = (one + x) * 0.5f;
+		p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+		q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+		s = sqrtf(z);
+		r = p / q;
+		w = r * s - pio2_lo;
+		return pi - 2.0f * (s + w);
+	}
+	z = (one - x) * 0.5f;                                     // x > 0.5
+	s = sqrtf(z);
+	df = __int_as_float(__float_as_int(s) & 0xfffff000);
+	c = (z - df * df) / (s + df);
+	p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+	q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+	r = p / q;
+	w = r * s + c;
+	return 2.0f * (df + w);
 }
 
 // common.h:145-151

@@ -35,8 +35,8 @@ def test_bounds_intersect_bit_exact(gpu_ctx, g):
 @pytest.mark.parametrize("skip", [True, False])
 def test_bsdf_against_reference(agpt, gpu_ctx, g, skip):
     """BSDF::f / Pdf / Sample_f for every material family.  +,-,*,/,sqrt only => bit-exact except
-    where cos/sin enter (cosine-hemisphere lobes): those go through double on the device and
-    must agree to 1 ulp-level relative tolerance (2e-6)."""
+    where cos/sin enter (cosine-hemisphere lobes): the device evaluates glibc's sinf/cosf
+    algorithm, so those rows are expected bit-identical too (tolerance 2e-6 kept as the floor)."""
     want_all = g["bsdf_out_skip"] if skip else g["bsdf_out_all"]
     exact = total = 0
     for mat6, want in zip(g["bsdf_mats"], want_all):
@@ -50,7 +50,7 @@ def test_bsdf_against_reference(agpt, gpu_ctx, g, skip):
         assert ok.all(), np.argwhere(~ok)[:5]
         exact += int(np.all(bits(got) == bits(want), axis=1).sum()); total += len(got)
     print(f"Sample_f rows bit-identical: {exact}/{total}")
-    assert exact / total > 0.95
+    assert exact / total > 0.995
 
 
 def test_sphere_light_sampling(gpu_ctx, g):
@@ -60,4 +60,4 @@ def test_sphere_light_sampling(gpu_ctx, g):
     assert np.allclose(got[:, :6], want[:, :6], rtol=3e-6, atol=3e-6)
     exact = np.all(bits(got) == bits(want), axis=1).mean()
     print(f"Sphere::Sample rows bit-identical: {exact:.3f}")
-    assert exact > 0.9
+    assert exact > 0.995

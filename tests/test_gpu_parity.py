@@ -44,4 +44,7 @@ def test_radiance_rmse(agpt, ref, gpu_ctx, config, level, W, H):
     err = rel_rmse(got, want)
     exact = np.mean(np.all(got[..., :3].view(np.uint32) == want[..., :3].view(np.uint32), axis=-1))
     print(f"cfg{config}: rel-RMSE {err:.3e}, bit-identical pixels {exact:.4f}")
-    assert err <= 1e-3
+    assert err <= 1e-3                      # the north-star gate
+    # stronger than the gate: sin/cos/acos follow glibc's algorithms on the device, so whole
+    # paths -- and with the same summation order the accumulators -- come out bit-identical
+    assert exact >= 0.999
