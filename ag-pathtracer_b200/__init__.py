@@ -7,6 +7,6 @@ a hyphen, so tests and bench load this package through ``importlib`` under the m
 ``agpt_b200`` (see ``tests/conftest.py`` / ``__graft_entry__.py``).
 """
 from .binding import (AgptError, Context, HostScene, HostTracer, Material, Stats, FLAG_COUNTERS, FLAG_TIMING,  # noqa: F401
-                      FLAG_FAST_BOXES, MAT_DISNEY, MAT_MIRROR, HIT_DTYPE, config_defaults, core, device_count, host,
+                      FLAG_STRICT_BOXES, MAT_DISNEY, MAT_MIRROR, HIT_DTYPE, config_defaults, core, device_count, host,
                       lib_paths, make_material)
 from . import multigpu  # noqa: F401,E402

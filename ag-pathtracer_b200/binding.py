@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 FLAG_COUNTERS = 1
 FLAG_TIMING = 2
-FLAG_FAST_BOXES = 4
+FLAG_STRICT_BOXES = 4
 
 MAT_DISNEY = 1
 MAT_MIRROR = 2

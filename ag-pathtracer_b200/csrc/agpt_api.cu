@@ -138,6 +138,22 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 
 static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+// ---- launch helpers: template flags from run-time flags --------------------------------------
+static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, int n, unsigned long long* cnt) {
+	if (count) { if (strictBoxes) k_trace_closest<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+	else { if (strictBoxes) k_trace_closest<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+}
+static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, int n, unsigned long long* cnt) {
+	if (count) { if (strictBoxes) k_trace_any<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+	else { if (strictBoxes) k_trace_any<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+}
+template <bool ANY>
+static void LaunchTable(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const float4* o, const float4* d, int n, agpt_hit* out, unsigned long long* cnt) {
+	if (count) { if (strictBoxes) k_trace_table<ANY, true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); else k_trace_table<ANY, true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); }
+	else { if (strictBoxes) k_trace_table<ANY, false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); else k_trace_table<ANY, false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); }
+}
+
+
 extern "C" {
 
 const char* agpt_last_error(void) { return g_error.c_str(); }
@@ -349,7 +365,7 @@ int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
 // ---- the wave loop -------------------------------------------------------------------------
 // Runs `n` already-generated paths (slots 0..n-1, queues A filled by k_generate) to completion.
 static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max_depth, int rr_depth_arg, uint32_t flags) {
-	const bool count = flags & AGPT_FLAG_COUNTERS, timing = flags & AGPT_FLAG_TIMING;
+	const bool count = flags & AGPT_FLAG_COUNTERS, timing = flags & AGPT_FLAG_TIMING, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
 	WaveQueues q[2];
 	for (int k = 0; k < 2; k++) {
 		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
@@ -362,14 +378,12 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	while (nActive > 0) {
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
 		if (nClosest > 0) {
-			if (count) k_trace_closest<true><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, cntClosest);
-			else k_trace_closest<false><<<Blocks(nClosest, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].closest, nClosest, cntClosest);
+			LaunchClosest(count, strictBoxes, Blocks(nClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, q[cur].closest, nClosest, cntClosest);
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (nShadow > 0) {
-			if (count) k_trace_any<true><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, cntAny);
-			else k_trace_any<false><<<Blocks(nShadow, AGPT_TRACE_THREADS), AGPT_TRACE_THREADS, 0, c->stream>>>(sc, ps, q[cur].shadow, nShadow, cntAny);
+			LaunchAny(count, strictBoxes, Blocks(nShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, q[cur].shadow, nShadow, cntAny);
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
@@ -447,16 +461,10 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 static int TraceTable(agpt_ctx* c, const DScene& sc, const float4* rayO, const float4* rayD, int n, int any_hit, uint32_t flags, agpt_hit* out_host) {
 	DevBuf<agpt_hit> out;
 	CU(out.Alloc(n));
-	const bool count = flags & AGPT_FLAG_COUNTERS;
+	const bool count = flags & AGPT_FLAG_COUNTERS, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
 	int blocks = Blocks(n, AGPT_TRACE_THREADS);
-	if (any_hit) {
-		if (count) k_trace_table<true, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
-		else k_trace_table<true, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
-	}
-	else {
-		if (count) k_trace_table<false, true><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
-		else k_trace_table<false, false><<<blocks, AGPT_TRACE_THREADS, 0, c->stream>>>(sc, rayO, rayD, n, out.p, c->traceCounters.p);
-	}
+	if (any_hit) LaunchTable<true>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
+	else LaunchTable<false>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
 	CU(cudaMemcpyAsync(out_host, out.p, (size_t)n * sizeof(agpt_hit), cudaMemcpyDeviceToHost, c->stream));

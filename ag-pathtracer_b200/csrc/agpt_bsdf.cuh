@@ -413,3 +413,138 @@ __device__ __forceinline__ float PowerHeuristic(int nf, float fPdf, int ng, floa
 	float f = nf * fPdf, g = ng * gPdf;
 	return (f * f) / (f * f + g * g);
 }
+
+// ---------------------------------------------------------------------------------------
+// Fused per-vertex evaluation used by the shade kernel.
+//
+// One path vertex needs the BSDF at three directions: the light sample (BSDF::f + BSDF::Pdf,
+// integrator.h:46-47), the MIS sample and the continuation sample (BSDF::Sample_f twice,
+// integrator.h:66,174 -- each re-evaluates every lobe's f and Pdf at the sampled direction,
+// reflection.h:156-171).  Evaluated through BSDF_f / BSDF_Pdf / BSDF_Sample_f above that is
+// four copies of the microfacet code and ~28 K SASS instructions in k_shade, which made the
+// kernel instruction-fetch bound (ncu: stall_no_instruction dominant).  Here the terms that
+// depend on wo only (local wo, Schlick weight, G1(wo)) are computed once per vertex and ONE
+// out-of-line evaluator returns, for a direction, the summed lobe values and the two distinct
+// lobe pdfs.  Every value is produced by the same operations in the same order as the
+// per-function restatement above (which the probe kernels keep testing against the reference),
+// so results stay bit-identical.
+// ---------------------------------------------------------------------------------------
+struct VertexBsdf {
+	DBSDF b;
+	float3 woW, wo;          // outgoing direction, world and shading space
+	float absCosO, Fo, G1o;  // |cos theta_o|, SchlickWeight(|cos theta_o|), G1(wo)
+	bool woOk;               // wo.z != 0 (BSDF::f / Pdf / Sample_f return 0 otherwise)
+	int nLobes;              // non-specular lobes: diffuse, retro, microfacet
+};
+__device__ __forceinline__ void VertexBsdfInit(VertexBsdf& v, const DSurface& si, const agpt_material* m, float3 woW) {
+	v.b = MakeBSDF(si, m);
+	v.woW = woW;
+	v.wo = WorldToLocal(v.b, woW);
+	v.woOk = v.wo.z != 0;
+	v.absCosO = AbsCosTheta(v.wo);
+	v.Fo = SchlickWeight(v.absCosO);
+	v.G1o = (m->lobes & AGPT_LOBE_MICROFACET) ? TR_G1(m->alpha_x, m->alpha_y, v.wo) : 0.f;
+	v.nLobes = ((m->lobes & AGPT_LOBE_DIFFUSE) ? 1 : 0) + ((m->lobes & AGPT_LOBE_RETRO) ? 1 : 0) + ((m->lobes & AGPT_LOBE_MICROFACET) ? 1 : 0);
+}
+
+struct LobeEval {
+	float3 f;          // sum of the non-specular lobes' f(wo, wi) in bxdfs[] order (caller applies `reflect`)
+	float pdfCos;      // BxDF::Pdf of a cosine-sampled lobe (reflection.h:16-18)
+	float pdfMicro;    // MicrofacetReflection::Pdf (reflection.h:67-71)
+};
+__device__ __noinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEval& out) {
+	const agpt_material& m = *v.b.mat;
+	const float absCosI = AbsCosTheta(wi);
+	const bool same = SameHemisphere(v.wo, wi);
+	out.pdfCos = same ? absCosI * AGPT_INVPI : 0;
+	out.pdfMicro = 0;
+	float3 f = f3(0.f);
+	float3 wh = wi + v.wo;
+	const bool whZero = wh.x == 0 && wh.y == 0 && wh.z == 0;
+	wh = normalize(wh);
+	const float Fi = SchlickWeight(absCosI);
+	const float3 R = f3(m.diffuse_r);
+	if (m.lobes & AGPT_LOBE_DIFFUSE) f += R * AGPT_INVPI * (1 - v.Fo / 2) * (1 - Fi / 2);                 // disney.h:27-34
+	if (m.lobes & AGPT_LOBE_RETRO) {                                                                    // disney.h:42-54
+		float3 fr = f3(0.f);
+		if (!whZero) {
+			float cosThetaD = dot(wi, wh);
+			float Rr = 2 * m.roughness * cosThetaD * cosThetaD;
+			fr = R * AGPT_INVPI * Rr * (v.Fo + Fi + v.Fo * Fi * (Rr - 1));
+		}
+		f += fr;
+	}
+	if (m.lobes & AGPT_LOBE_MICROFACET) {                                                               // reflection.h:42-54,67-71
+		float3 fm = f3(0.f);
+		if (!(absCosI == 0 || v.absCosO == 0) && !whZero) {
+			float3 F = DisneyFresnel(m, dot(wi, Faceforward(wh, f3(0, 0, 1))));
+			float D = TR_D(m.alpha_x, m.alpha_y, wh);
+			float G = v.G1o * TR_G1(m.alpha_x, m.alpha_y, wi);
+			fm = f3(1.f) * D * G * F / (4 * absCosI * v.absCosO);
+			if (same) out.pdfMicro = D * v.G1o * absdot(v.wo, wh) / v.absCosO / (4 * dot(v.wo, wh));
+		}
+		f += fm;
+	}
+	out.f = f;
+}
+
+struct DirSample {
+	float3 wi;        // sampled direction, shading space
+	float3 fSpec;     // value of a specular lobe (reflection.cpp:13-17)
+	float pdf;        // pdf of the chosen lobe alone
+	int lobe;         // AGPT_LOBE_* that was sampled
+	int matching;     // lobes that took part in the choice
+	bool ok;          // false where BSDF::Sample_f returns black (reflection.h:130-157)
+};
+// First half of BSDF::Sample_f: choose the lobe, remap u, sample its direction (reflection.h:126-157).
+__device__ __noinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, bool skipSpecular, DirSample& s) {
+	const agpt_material& m = *v.b.mat;
+	int lobes[4];
+	int matching = LobeList(m, skipSpecular, lobes);
+	s.ok = false; s.pdf = 0; s.lobe = 0; s.matching = matching; s.wi = f3(0.f); s.fSpec = f3(0.f);
+	if (matching == 0) return;
+	int comp = min((int)floorf(u.x * matching), matching - 1);
+	int lobe = lobes[comp];
+	float2 uR = make_float2(smin(u.x * matching - comp, AGPT_ONE_MINUS_EPS), u.y);
+	s.lobe = lobe;
+	if (!v.woOk) return;
+	float3 wo = v.wo, wi = f3(0.f);
+	float pdf = 0;
+	if (lobe == AGPT_LOBE_SPECULAR) {
+		wi = f3(-wo.x, -wo.y, wo.z);
+		pdf = 1;
+		s.fSpec = f3(1.f) * f3(m.mirror_r) / AbsCosTheta(wi);
+	}
+	else if (lobe == AGPT_LOBE_MICROFACET) {
+		float3 wh = TR_Sample_wh(m.alpha_x, m.alpha_y, wo, uR);
+		if (!(dot(wo, wh) < 0)) {
+			wi = Reflect(wo, wh);
+			if (SameHemisphere(wo, wi))
+				pdf = TR_D(m.alpha_x, m.alpha_y, wh) * v.G1o * absdot(wo, wh) / v.absCosO / (4 * dot(wo, wh));
+		}
+	}
+	else {
+		wi = CosineSampleHemisphere(uR);
+		if (wo.z < 0) wi.z *= -1;
+		pdf = Cosine_Pdf(wo, wi);
+	}
+	if (pdf == 0) return;
+	s.wi = wi; s.pdf = pdf; s.ok = true;
+}
+// Second half of BSDF::Sample_f: overall pdf over the matching lobes and the BSDF value (reflection.h:158-171).
+__device__ __forceinline__ float3 FinishSample(const VertexBsdf& v, const DirSample& s, const LobeEval& e, float3 wiW, float* pdfOut) {
+	const agpt_material& m = *v.b.mat;
+	const bool specular = s.lobe == AGPT_LOBE_SPECULAR;
+	float pdf = s.pdf;
+	if (!specular && s.matching > 1) {
+		if ((m.lobes & AGPT_LOBE_DIFFUSE) && s.lobe != AGPT_LOBE_DIFFUSE) pdf += e.pdfCos;
+		if ((m.lobes & AGPT_LOBE_RETRO) && s.lobe != AGPT_LOBE_RETRO) pdf += e.pdfCos;
+		if ((m.lobes & AGPT_LOBE_MICROFACET) && s.lobe != AGPT_LOBE_MICROFACET) pdf += e.pdfMicro;
+	}
+	if (s.matching > 1) pdf /= s.matching;
+	*pdfOut = pdf;
+	if (specular) return s.fSpec;
+	bool reflect = dot(wiW, v.b.ng) * dot(v.woW, v.b.ng) > 0;
+	return reflect ? e.f : f3(0.f);
+}
+

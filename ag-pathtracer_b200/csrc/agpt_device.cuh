@@ -235,6 +235,43 @@ __device__ __forceinline__ bool BoundsIntersect(float3 bmin, float3 bmax, float3
 	return !((tmax * 1.00000024f) < tmin);
 }
 
+// ---------------------------------------------------------------------------------------
+// Exact-filtered slab test.  Bounds::Intersect costs six IEEE divisions per box.  What the
+// walk needs from it are DECISIONS -- box hit or not, and which child is nearer -- not the
+// distances themselves.  q~ = (b - O) * fl(1/D) differs from the reference's fl((b - O)/D) by
+// at most 3 * 2^-24 relative (same numerator, two roundings against one), signs and exact
+// zeros are preserved, and min/max keep that bound.  So each decision is first taken on the
+// cheap values with a guard band of 2^-19 relative -- 8x the worst case incl. the rounding of
+// tmax*1.00000024f -- and only when a comparison falls inside the band is the pair re-done
+// with the reference arithmetic (BoundsIntersect above).  Decisions, hence traversal order,
+// visit counts and hits, are identical to the strict walk; tests assert exactly that.
+// Rays with a direction component below 1e-18 in magnitude (or zero) always take the
+// reference arithmetic, as do non-finite inputs.
+// ---------------------------------------------------------------------------------------
+#define AGPT_GUARD 1.9073486328125e-06f      // 2^-19
+
+__device__ __forceinline__ void SlabApprox(float3 bmin, float3 bmax, float3 O, float3 rD, float rayT, float& tmin, float& tmax) {
+	float ax = (bmin.x - O.x) * rD.x, bx = (bmax.x - O.x) * rD.x;
+	float ay = (bmin.y - O.y) * rD.y, by = (bmax.y - O.y) * rD.y;
+	float az = (bmin.z - O.z) * rD.z, bz = (bmax.z - O.z) * rD.z;
+	tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+	tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), rayT));
+}
+// 1 = certainly hit, 0 = certainly missed, -1 = inside the guard band (ask the reference arithmetic)
+__device__ __forceinline__ int SlabDecision(float tmin, float tmax) {
+	float T = tmax * 1.00000024f;
+	if (T < tmin * (1.0f - AGPT_GUARD)) return 0;
+	if (T > tmin * (1.0f + AGPT_GUARD)) return 1;
+	return -1;
+}
+// 1 = right child certainly nearer (swap), 0 = certainly not, -1 = inside the guard band
+__device__ __forceinline__ int NearerDecision(float dl, float dr) {
+	if (dl == 0.0f && dr == 0.0f) return 0;          // origin inside both boxes: exact zeros on both sides
+	if (dr < dl * (1.0f - AGPT_GUARD)) return 1;
+	if (dr > dl * (1.0f + AGPT_GUARD)) return 0;
+	return -1;
+}
+
 // Moller-Trumbore of TriangleMesh::TriangleIntersect(P) (trianglemesh.cpp:7-43,117-155):
 // no culling, no epsilon; reject det==0, b1<0||b1>1, b2<0||b1+b2>1, t<=0||t>=ray.t.
 __device__ __forceinline__ bool TriangleTest(float3 v0, float3 v1, float3 v2, float3 O, float3 D, float rayT,

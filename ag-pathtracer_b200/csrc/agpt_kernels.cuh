@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 }
 
 // ---- trace kernels ---------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, int count,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc,
 		d = kind ? ps.misD[path] : ps.rayD[path];
 	}
 	HitRecord hit;
-	TraceScene<false, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	TraceScene<false, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) {
 		if (kind == 0) {
 			ps.hitA[path] = make_float4(hit.t, hit.b1, hit.b2, __int_as_float(hit.prim));
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc,
 	if (COUNT) FlushCounters(cnt, counters);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, int count,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -170,13 +170,13 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_any(DScene sc, Pat
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = ps.shO[path]; d = ps.shD[path]; }
 	HitRecord hit;
-	bool occluded = TraceScene<true, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	bool occluded = TraceScene<true, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) ps.shadowOccluded[path] = occluded ? 1 : 0;
 	if (COUNT) FlushCounters(cnt, counters);
 }
 
 // Standalone rays (agpt_trace_rays / agpt_trace_primary): hit table out.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool FAST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
 		int count, agpt_hit* out, unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = rayO[i]; d = rayD[i]; }
 	HitRecord hit;
-	bool found = TraceScene<ANY, COUNT>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	bool found = TraceScene<ANY, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) {
 		agpt_hit h;
 		h.found = found ? 1u : 0u;
@@ -291,44 +291,50 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 				}
 				else {
 					const agpt_material* mat = sc.mats + prim.material;
-					DBSDF bsdf = MakeBSDF(si, mat);
 					float3 wo = -D;
+					VertexBsdf vb;
+					VertexBsdfInit(vb, si, mat, wo);
 					uint32_t rng = ps.rng[path];
+					const bool doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
 
-					// (3) UniformSampleOneLight (integrator.h:95-105) unless perfectly specular (:165)
-					if (!BSDF_IsPerfectlySpecular(bsdf) && sc.n_lights > 0) {
+					// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
+					// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
+					// (float2 arguments are evaluated right to left: .y first), then the two extra
+					// draws UniformInfiniteLight::Sample_Li makes (lights.cpp:15-24), then u (:171).
+					int numLight = 0;
+					float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0);
+					float3 wiL = f3(0.f), Li = f3(0.f), lemit = f3(0.f);
+					float lightPdf = 0;
+					DRay vis;
+					vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
+					int lightType = -1, lightPrimType = -1, lightPayload = 0;
+					if (doNee) {
 						int nLights = sc.n_lights;
-						int numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
-						float2 uLight, uScattering;
-						uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);            // right-to-left argument order
+						numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
+						uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);
 						uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
 						const agpt_light& light = sc.lights[numLight];
-						float3 lemit = f3(light.lemit);
-
-						// EstimateDirect (integrator.h:38-93): light sampling strategy
-						float3 wi = f3(0.f);
-						float lightPdf = 0, scatteringPdf = 0;
-						float3 Li = f3(0.f);
-						DRay vis;
-						vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
-						if (light.type == AGPT_LIGHT_AREA) {
+						lemit = f3(light.lemit);
+						lightType = light.type;
+						if (lightType == AGPT_LIGHT_AREA) {
 							// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
 							const agpt_prim& lp = sc.prims[light.prim];
+							lightPrimType = lp.type; lightPayload = lp.payload;
 							if (lp.type == AGPT_PRIM_SPHERE) {
 								float3 pS, nS;
 								SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
 								if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
 								else {
-									wi = pS - si.p;
-									float dist = length(wi);
-									wi /= dist;
-									vis = MakeRay(si.p + AGPT_EPSILON * wi, wi, dist - 10 * AGPT_EPSILON);
+									wiL = pS - si.p;
+									float dist = length(wiL);
+									wiL /= dist;
+									vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
 									Li = lemit;
 								}
 							}
 						}
 						else {
-							// UniformInfiniteLight::Sample_Li (lights.cpp:15-24): ignores u, draws 2 more
+							// UniformInfiniteLight::Sample_Li: RandomInHemisphere(shading.n), pdf 1/2pi
 							float a = 1 - 2 * RandomFloat(rng);
 							float b = sqrtf(1 - a * a);
 							float phi = 2 * AGPT_PI * RandomFloat(rng);
@@ -336,14 +342,61 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 							rsincos(phi, &sphi, &cphi);
 							float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
 							if (dot(v, si.sn) < 0) v = -v;
-							wi = v;
+							wiL = v;
 							lightPdf = AGPT_INV2PI;
-							vis = MakeRay(si.p + AGPT_EPSILON * wi, wi);
+							vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL);
 							Li = lemit;
 						}
-						if (lightPdf > 0 && !IsBlack(Li)) {
-							float3 f = BSDF_f(bsdf, wo, wi, true) * absdot(wi, si.sn);
-							scatteringPdf = BSDF_Pdf(bsdf, wo, wi, true);
+					}
+					float2 u;
+					u.y = RandomFloat(rng); u.x = RandomFloat(rng);
+
+					// ---- directions: [0] light sample, [1] MIS sample, [2] continuation sample ----
+					const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
+					DirSample smp[2];
+#pragma unroll 1
+					for (int k = 0; k < 2; k++) {
+						bool want = k == 0 ? doNee : true;
+						if (want) SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, smp[k]);
+						else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
+					}
+					// ---- one evaluator, three directions ----
+					float3 fDir[3];
+					float pdfDir[3];
+					float3 wiWorld[3];
+#pragma unroll 1
+					for (int k = 0; k < 3; k++) {
+						fDir[k] = f3(0.f); pdfDir[k] = 0.f; wiWorld[k] = f3(0.f);
+						bool need = k == 0 ? (evalLight && vb.woOk) : (smp[k - 1].ok && smp[k - 1].lobe != AGPT_LOBE_SPECULAR);
+						float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : smp[k - 1].wi;
+						LobeEval ev;
+						ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
+						if (need) EvalLobes(vb, wiLoc, ev);
+						if (k == 0) {
+							if (need) {
+								// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
+								bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
+								fDir[0] = reflect ? ev.f : f3(0.f);
+								float p = 0.f;
+								if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
+								if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
+								if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
+								pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
+							}
+							wiWorld[0] = wiL;
+						}
+						else if (smp[k - 1].ok) {
+							wiWorld[k] = LocalToWorld(vb.b, smp[k - 1].wi);
+							fDir[k] = FinishSample(vb, smp[k - 1], ev, wiWorld[k], &pdfDir[k]);
+						}
+					}
+
+					// (3) EstimateDirect (integrator.h:38-93)
+					if (doNee) {
+						float scatteringPdf = 0;
+						if (evalLight) {
+							float3 f = fDir[0] * absdot(wiL, si.sn);
+							scatteringPdf = pdfDir[0];
 							if (!IsBlack(f)) {
 								float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
 								float3 term = f * Li * weight / lightPdf;
@@ -353,17 +406,14 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 								emitShadow = true;
 							}
 						}
-						// BSDF sampling strategy with MIS (integrator.h:62-90)
-						{
-							float3 wim = f3(0.f);
-							float3 f = BSDF_Sample_f(bsdf, wo, &wim, uScattering, &scatteringPdf, true, nullptr);
+						if (smp[0].ok) {
+							float3 wim = wiWorld[1];
+							float3 f = fDir[1];
+							scatteringPdf = pdfDir[1];
 							f *= absdot(wim, si.sn);
 							if (!IsBlack(f) && scatteringPdf > 0) {
 								float lp;
-								if (light.type == AGPT_LIGHT_AREA) {
-									const agpt_prim& lpr = sc.prims[light.prim];
-									lp = lpr.type == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lpr.payload], si.p) : 0.f;
-								}
+								if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
 								else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
 								if (lp != 0) {
 									float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
@@ -379,14 +429,12 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 						if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
 					}
 
-					// (4) sample the BSDF for the new direction (integrator.h:169-177)
-					float2 u;
-					u.y = RandomFloat(rng); u.x = RandomFloat(rng);
-					float3 wi = f3(0.f);
-					float pdf = 0.f;
-					bool sampledSpecular = false;
-					float3 f = BSDF_Sample_f(bsdf, wo, &wi, u, &pdf, false, &sampledSpecular);
-					bool alive = !(IsBlack(f) || pdf == 0);
+					// (4) the new path direction (integrator.h:169-185)
+					float3 wi = wiWorld[2];
+					float pdf = pdfDir[2];
+					float3 f = fDir[2];
+					bool sampledSpecular = smp[1].lobe == AGPT_LOBE_SPECULAR;
+					bool alive = smp[1].ok && !(IsBlack(f) || pdf == 0);
 					if (alive) {
 						beta *= f * absdot(wi, si.sn) / pdf;
 						specularBounce = sampledSpecular;

@@ -67,7 +67,7 @@ __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, in
 // `continue`d early run ahead as separate fragments (measured: 2.3-3.1 of 32 threads active
 // per instruction with the naive while/continue form).  `lane` is false for threads past the
 // end of the queue; they must still call (full-mask votes).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool FAST>
 __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, float3 O, float3 D, float& rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	bool found = false;
@@ -87,6 +87,10 @@ __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, floa
 	}
 
 	unsigned local[AGPT_STACK_LOCAL];
+	// exact-filtered slab test (agpt_device.cuh): reciprocal direction, valid only for sane components
+	float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
+		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
 	NodeBox root = LoadNode(mesh.nodes, 0);
 	float dist;
 	if (COUNT && lane) cnt.box_tests++;
@@ -101,12 +105,25 @@ __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, floa
 				NodeBox l = LoadNode(mesh.nodes, (int)cur), r = LoadNode(mesh.nodes, (int)cur + 1);
 				if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
 				float dl, dr;
-				bool hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
-				bool hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+				bool hl, hr, swapKids;
+				bool strict = !filterOk;
+				if (!strict) {
+					float xl, xr;
+					SlabApprox(l.bmin, l.bmax, O, rD, rayT, dl, xl);
+					SlabApprox(r.bmin, r.bmax, O, rD, rayT, dr, xr);
+					int cl = SlabDecision(dl, xl), cr = SlabDecision(dr, xr);
+					int cs = (ANY || cl != 1 || cr != 1) ? 0 : NearerDecision(dl, dr);
+					hl = cl == 1; hr = cr == 1; swapKids = cs == 1;
+					strict = (cl | cr | cs) < 0;       // some comparison fell inside the guard band
+				}
+				if (strict) {
+					hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
+					hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+					// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
+					// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
+					swapKids = ANY ? false : (dr < dl);
+				}
 				unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
-				// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
-				// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
-				bool swapKids = ANY ? false : (dr < dl);
 				if (hl && hr) {
 					unsigned farE = swapKids ? el : er;
 					if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
@@ -149,7 +166,7 @@ __device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, floa
 
 // Scene::Intersect (ANY=false) / Scene::IntersectP (ANY=true): primitives in list order.
 // Every lane of the warp must call (lane=false for threads without a ray).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool FAST>
 __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D, float rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
@@ -175,7 +192,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 			}
 		}
 		else {
-			if (TraceMesh<ANY, COUNT>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			if (TraceMesh<ANY, COUNT, FAST>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
 		}
 	}
 	return found;

@@ -161,7 +161,8 @@ typedef struct agpt_stats {
 enum {
 	AGPT_FLAG_COUNTERS = 1u,      /* count node visits / box / triangle tests (slower kernels) */
 	AGPT_FLAG_TIMING = 2u,        /* bracket every kernel class with CUDA events (serialises) */
-	AGPT_FLAG_FAST_BOXES = 4u     /* result-identical reciprocal slab test instead of the strict one */
+	AGPT_FLAG_STRICT_BOXES = 4u   /* every slab test with the reference's six IEEE divisions; the default is the
+	                                 exact-filtered test (same decisions, divisions only inside a guard band) */
 };
 
 /* ---- lifecycle --------------------------------------------------------------------- */
