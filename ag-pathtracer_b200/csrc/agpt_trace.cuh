@@ -57,108 +57,128 @@ __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, in
 	return n;
 }
 
-// One mesh.  `stack` points at this thread's shared-memory column (stride = blockDim.x).
-// ANY: stop at the first accepted triangle.  Otherwise updates hit / rayT.
+// A RUN of consecutive mesh primitives [p0, p1) of Scene::primitives.  `stack` points at this
+// thread's shared-memory column (stride = blockDim.x).  ANY: stop at the first accepted
+// triangle.  Otherwise updates hit / rayT.
 //
 // Convergence: the walk is a WARP-SYNCHRONOUS loop.  All 32 lanes stay in the loop until
 // every lane is done (`__any_sync` on the loop condition); a finished or invalid lane is
 // predicated off.  The loop has one back edge and every path through the body merges before
-// it, so the hardware re-converges the warp once per node step instead of letting lanes that
+// it, so the hardware re-converges the warp once per step instead of letting lanes that
 // `continue`d early run ahead as separate fragments (measured: 2.3-3.1 of 32 threads active
-// per instruction with the naive while/continue form).  `lane` is false for threads past the
-// end of the queue; they must still call (full-mask votes).
+// per instruction with the naive while/continue form, 7-23 with this one).
+//
+// Each lane walks the meshes of the run in list order on its own: a lane whose ray misses a
+// mesh's root box (bvhtrimesh.h:187) moves on to the next mesh at once instead of idling
+// until the slowest lane of the warp has finished that mesh.  Per ray the sequence of box
+// and triangle tests is exactly the reference's; only the interleaving between rays differs.
+// `lane` is false for threads without a ray; they must still call (full-mask votes).
 template <bool ANY, bool COUNT, bool FAST>
-__device__ __forceinline__ bool TraceMesh(const DMesh& mesh, int primIndex, float3 O, float3 D, float& rayT, HitRecord& hit,
+__device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, float3 O, float3 D, float& rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	bool found = false;
-	if (mesh.nodes == nullptr) {
-		// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
-		for (int j = 0; j < mesh.n_tris; j++) {
-			float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
-			float t, b1, b2;
-			bool test = lane && !(ANY && found);
-			if (COUNT && test) cnt.tri_tests++;
-			if (test && a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
-				if (!ANY) { rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j; }
-				found = true;
-			}
-		}
-		return found;
-	}
-
 	unsigned local[AGPT_STACK_LOCAL];
 	// exact-filtered slab test (agpt_device.cuh): reciprocal direction, valid only for sane components
-	float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
 	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
 		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
-	NodeBox root = LoadNode(mesh.nodes, 0);
-	float dist;
-	if (COUNT && lane) cnt.box_tests++;
-	bool active = lane && BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist);
-	unsigned cur = EncodeNode(0, root.first, root.count);
+	int mp = p0;                     // this lane's current mesh primitive
+	bool inside = false;             // walking mesh mp (else: about to enter it)
+	const float4* nodes = nullptr;
+	const float4* tris = nullptr;
+	unsigned cur = 0;
 	int sp = 0;
-	while (__any_sync(0xffffffffu, active)) {
-		if (active) {
-			bool pop = true;
-			if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
-				// interior: fetch the sibling pair (64 B), test both boxes
-				NodeBox l = LoadNode(mesh.nodes, (int)cur), r = LoadNode(mesh.nodes, (int)cur + 1);
-				if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
-				float dl, dr;
-				bool hl, hr, swapKids;
-				bool strict = !filterOk;
-				if (!strict) {
-					float xl, xr;
-					SlabApprox(l.bmin, l.bmax, O, rD, rayT, dl, xl);
-					SlabApprox(r.bmin, r.bmax, O, rD, rayT, dr, xr);
-					int cl = SlabDecision(dl, xl), cr = SlabDecision(dr, xr);
-					int cs = (ANY || cl != 1 || cr != 1) ? 0 : NearerDecision(dl, dr);
-					hl = cl == 1; hr = cr == 1; swapKids = cs == 1;
-					strict = (cl | cr | cs) < 0;       // some comparison fell inside the guard band
+	bool active = lane;
+	while (__any_sync(0xffffffffu, active && mp < p1)) {
+		if (active && mp < p1) {
+			if (!inside) {
+				// enter mesh mp: root bounds test (BVHTriMesh::Intersect, bvhtrimesh.h:185-191)
+				const DMesh& mesh = sc.meshes[sc.prims[mp].payload];
+				nodes = mesh.nodes; tris = mesh.tris;
+				if (nodes == nullptr) {
+					// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
+					for (int j = 0; j < mesh.n_tris; j++) {
+						float4 a = __ldg(tris + 3 * j), b = __ldg(tris + 3 * j + 1), c = __ldg(tris + 3 * j + 2);
+						if (COUNT) cnt.tri_tests++;
+						float t, b1, b2;
+						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+							found = true;
+							if (ANY) break;
+							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
+						}
+					}
+					mp++;
 				}
-				if (strict) {
-					hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
-					hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
-					// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
-					// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
-					swapKids = ANY ? false : (dr < dl);
+				else {
+					NodeBox root = LoadNode(nodes, 0);
+					float dist;
+					if (COUNT) cnt.box_tests++;
+					if (BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist)) { cur = EncodeNode(0, root.first, root.count); sp = 0; inside = true; }
+					else mp++;
 				}
-				unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
-				if (hl && hr) {
-					unsigned farE = swapKids ? el : er;
-					if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
-					sp++;
-					cur = swapKids ? er : el;
-					pop = false;
-				}
-				else if (hl || hr) { cur = hl ? el : er; pop = false; }
 			}
 			else {
-				int first, count;
-				if (cur & AGPT_ENT_LEAF1) { first = (int)(cur & 0x7fffffffu); count = 1; }
-				else {
-					NodeBox n = LoadNode(mesh.nodes, (int)(cur & 0x3fffffffu));
-					first = n.first; count = n.count;
+				bool pop = true;
+				if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
+					// interior: fetch the sibling pair (64 B), test both boxes
+					NodeBox l = LoadNode(nodes, (int)cur), r = LoadNode(nodes, (int)cur + 1);
+					if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
+					float dl, dr;
+					bool hl, hr, swapKids;
+					bool strict = !filterOk;
+					if (!strict) {
+						float xl, xr;
+						SlabApprox(l.bmin, l.bmax, O, rD, rayT, dl, xl);
+						SlabApprox(r.bmin, r.bmax, O, rD, rayT, dr, xr);
+						int cl = SlabDecision(dl, xl), cr = SlabDecision(dr, xr);
+						int cs = (ANY || cl != 1 || cr != 1) ? 0 : NearerDecision(dl, dr);
+						hl = cl == 1; hr = cr == 1; swapKids = cs == 1;
+						strict = (cl | cr | cs) < 0;       // some comparison fell inside the guard band
+					}
+					if (strict) {
+						hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
+						hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+						// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
+						// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
+						swapKids = ANY ? false : (dr < dl);
+					}
+					unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
+					if (hl && hr) {
+						unsigned farE = swapKids ? el : er;
+						if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
+						sp++;
+						cur = swapKids ? er : el;
+						pop = false;
+					}
+					else if (hl || hr) { cur = hl ? el : er; pop = false; }
 				}
-				for (int j = first; j < first + count; j++) {
-					float4 a = __ldg(mesh.tris + 3 * j), b = __ldg(mesh.tris + 3 * j + 1), c = __ldg(mesh.tris + 3 * j + 2);
-					if (COUNT) cnt.tri_tests++;
-					float t, b1, b2;
-					if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
-						found = true;
-						if (ANY) break;
-						rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = primIndex; hit.slot = j;
+				else {
+					int first, count;
+					if (cur & AGPT_ENT_LEAF1) { first = (int)(cur & 0x7fffffffu); count = 1; }
+					else {
+						NodeBox n = LoadNode(nodes, (int)(cur & 0x3fffffffu));
+						first = n.first; count = n.count;
+					}
+					for (int j = first; j < first + count; j++) {
+						float4 a = __ldg(tris + 3 * j), b = __ldg(tris + 3 * j + 1), c = __ldg(tris + 3 * j + 2);
+						if (COUNT) cnt.tri_tests++;
+						float t, b1, b2;
+						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+							found = true;
+							if (ANY) break;
+							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
+						}
+					}
+				}
+				if (pop) {
+					if (sp == 0) { inside = false; mp++; }
+					else {
+						sp--;
+						cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
 					}
 				}
 			}
 			if (ANY && found) active = false;
-			else if (pop) {
-				if (sp == 0) active = false;
-				else {
-					sp--;
-					cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
-				}
-			}
 		}
 	}
 	return found;
@@ -171,7 +191,8 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
 	bool found = false;
-	for (int p = 0; p < sc.n_prims; p++) {
+	int p = 0;
+	while (p < sc.n_prims) {
 		agpt_prim prim = sc.prims[p];
 		bool test = lane && !(ANY && found);
 		if (ANY && !__any_sync(0xffffffffu, test)) break;     // warp-uniform early out of IntersectP
@@ -182,6 +203,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
 				found = true;
 			}
+			p++;
 		}
 		else if (prim.type == AGPT_PRIM_PLANE) {
 			if (COUNT && test) cnt.analytic_tests++;
@@ -190,9 +212,13 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
 				found = true;
 			}
+			p++;
 		}
 		else {
-			if (TraceMesh<ANY, COUNT, FAST>(sc.meshes[prim.payload], p, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			int q = p + 1;                                     // run of consecutive mesh primitives
+			while (q < sc.n_prims && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
+			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			p = q;
 		}
 	}
 	return found;
