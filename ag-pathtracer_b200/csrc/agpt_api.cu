@@ -75,12 +75,16 @@ struct agpt_ctx {
 	DevBuf<int> i32[3];
 	DevBuf<uint32_t> u32[2];
 	DevBuf<int> queues[6];        // closest A/B (2*cap), shadow A/B, active A/B
+	DevBuf<int> sortedClosest;    // closest queue in bucket order (2*cap)
+	DevBuf<unsigned char> keys[2];
+	DevBuf<int> hist;             // 2 x AGPT_BUCKETS histogram (A/B) + offsets + running
 	DevBuf<int> counts;           // 2 x 3
 	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned, 3 ints
 
 	agpt_stats stats;
+	bool bucketRays = true;       // bucket pass on the closest-hit queue (AGPT_BUCKET_RAYS=0 turns it off)
 };
 
 static const size_t kMaxPathsPerBatch = (size_t)1 << 23;   // 8.4 M path slots ~ 1.8 GB of wavefront state
@@ -111,6 +115,7 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	for (auto& b : c->i32) CU(b.Alloc(paths));
 	for (auto& b : c->u32) CU(b.Alloc(paths));
 	CU(c->queues[0].Alloc(2 * paths)); CU(c->queues[1].Alloc(2 * paths));
+	CU(c->sortedClosest.Alloc(2 * paths)); CU(c->keys[0].Alloc(2 * paths)); CU(c->keys[1].Alloc(2 * paths));
 	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths));
 	c->capacity = paths;
 	return AGPT_OK;
@@ -187,11 +192,13 @@ int agpt_create(int device, agpt_ctx** out) {
 	c->stream = c->ownStream;
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
+	CU(c->hist.Alloc(4 * AGPT_BUCKETS));
 	CU(c->traceCounters.Alloc(8));
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
 	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
 	CU(cudaMallocHost((void**)&c->hostCounts, 3 * sizeof(int)));
+	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	*out = c;
 	return AGPT_OK;
 }
@@ -207,6 +214,7 @@ int agpt_destroy(agpt_ctx* c) {
 	for (auto& b : c->i32) b.Free();
 	for (auto& b : c->u32) b.Free();
 	for (auto& b : c->queues) b.Free();
+	c->sortedClosest.Free(); c->keys[0].Free(); c->keys[1].Free(); c->hist.Free();
 	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
 	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
@@ -370,7 +378,12 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	for (int k = 0; k < 2; k++) {
 		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
 		q[k].counts = c->counts.p + 3 * k;
+		q[k].keys = c->keys[k].p; q[k].hist = c->hist.p + AGPT_BUCKETS * k;
 	}
+	int* bucketOffsets = c->hist.p + 2 * AGPT_BUCKETS;
+	int* bucketRunning = c->hist.p + 3 * AGPT_BUCKETS;
+	const bool bucketing = c->bucketRays;
+	const int* closestQueue = q[0].closest;     // wave 0: camera rays in pixel order
 	int nClosest = n, nShadow = 0, nActive = n, cur = 0;
 	float msClosest = 0, msAny = 0, msShade = 0;
 	unsigned long long* cntClosest = c->traceCounters.p;
@@ -378,7 +391,7 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	while (nActive > 0) {
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
 		if (nClosest > 0) {
-			LaunchClosest(count, strictBoxes, Blocks(nClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, q[cur].closest, nClosest, cntClosest);
+			LaunchClosest(count, strictBoxes, Blocks(nClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, nClosest, cntClosest);
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
@@ -387,6 +400,7 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
+		CU(cudaMemsetAsync(q[cur ^ 1].hist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = nActive; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
@@ -405,6 +419,14 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		}
 		nClosest = c->hostCounts[0]; nShadow = c->hostCounts[1]; nActive = c->hostCounts[2];
 		cur ^= 1;
+		closestQueue = q[cur].closest;
+		if (bucketing && nClosest > 0) {
+			// bucket pass: put rays that leave the same primitive in the same octant next to each other
+			k_bucket_scan<<<1, AGPT_BUCKETS, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
+			k_bucket_scatter<<<Blocks(nClosest, 256), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, nClosest, bucketOffsets, bucketRunning, c->sortedClosest.p);
+			c->stats.kernel_launches += 2;
+			closestQueue = c->sortedClosest.p;
+		}
 		c->stats.waves++;
 	}
 	c->stats.ms_trace_closest += msClosest; c->stats.ms_trace_any += msAny; c->stats.ms_shade += msShade;
@@ -427,7 +449,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
 	// evA/evC/evD are reused inside RunWaves when timing; the render bracket has its own pair
 	cudaEvent_t r0, r1;
 	CU(cudaEventCreate(&r0)); CU(cudaEventCreate(&r1));
@@ -484,7 +506,7 @@ int agpt_trace_primary(agpt_ctx* c, int sample, uint32_t flags, agpt_hit* out_ho
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
 	GenParams g;
 	memset(&g, 0, sizeof(g));
 	g.n = (int)wh; g.first_sample = sample; g.sample_stride = 1;
@@ -506,7 +528,7 @@ int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uin
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
 	DevBuf<float> rays;
 	DevBuf<uint32_t> seeds;
 	CU(rays.Upload(rays7, 7 * (size_t)n, c->stream));
@@ -530,7 +552,7 @@ static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, 
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
 	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;

@@ -42,8 +42,12 @@ struct PathState {
 	float4* Lout;        // finished radiance per path slot
 };
 
+#define AGPT_BUCKETS 64     // ray buckets: 3 bits direction octant | 3 bits of the primitive the ray leaves
+
 struct WaveQueues {
 	int* closest;        // entries path*2 + kind (0 = path ray, 1 = MIS ray)
+	unsigned char* keys; // bucket key of each closest-queue entry
+	int* hist;           // AGPT_BUCKETS counters: entries per bucket
 	int* shadow;         // entries path
 	int* active;         // paths that take part in the next shade
 	int* counts;         // [0] closest, [1] shadow, [2] active
@@ -62,6 +66,49 @@ __device__ __forceinline__ int WarpAppend(bool pred, int* counter) {
 	if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
 	base = __shfl_sync(0xffffffffu, base, 0);
 	return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// Ray bucket: rays that leave the same primitive in the same direction octant walk similar parts
+// of the trees in the same near/far order, so putting them next to each other in the queue
+// raises both the SIMT efficiency of the lockstep walk and the L1/L2 hit rate.
+__device__ __forceinline__ int RayBucket(float3 D, int fromPrim) {
+	return (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0) | ((fromPrim & 7) << 3);
+}
+// Histogram add with one atomic per distinct key per warp.  All 32 lanes must call.
+__device__ __forceinline__ void WarpHistAdd(bool pred, int key, int* hist) {
+	int lane = threadIdx.x & 31;
+	unsigned m = __match_any_sync(0xffffffffu, pred ? key : (AGPT_BUCKETS + lane));
+	if (pred && lane == __ffs(m) - 1) atomicAdd(hist + key, __popc(m));
+}
+
+// Bucket pass between shade and the next trace: exclusive scan of the histogram (one block) ...
+__global__ void k_bucket_scan(const int* hist, int* offsets, int* running) {
+	__shared__ int sh[AGPT_BUCKETS];
+	int i = threadIdx.x;
+	sh[i] = hist[i];
+	__syncthreads();
+	if (i == 0) {
+		int acc = 0;
+		for (int k = 0; k < AGPT_BUCKETS; k++) { int v = sh[k]; sh[k] = acc; acc += v; }
+	}
+	__syncthreads();
+	offsets[i] = sh[i];
+	running[i] = 0;
+}
+// ... and the scatter of the queue entries into bucket order (order inside a bucket is free:
+// every path's arithmetic is independent of its queue position).
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned char* __restrict__ keys, int count,
+		const int* __restrict__ offsets, int* running, int* __restrict__ out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool valid = i < count;
+	int lane = threadIdx.x & 31;
+	int key = valid ? keys[i] : (AGPT_BUCKETS + lane);
+	unsigned m = __match_any_sync(0xffffffffu, key);
+	int leader = __ffs(m) - 1;
+	int base = 0;
+	if (valid && lane == leader) base = atomicAdd(running + key, __popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (valid) out[offsets[key] + base + __popc(m & ((1u << lane) - 1u))] = in[i];
 }
 
 // ---- path generation: myapp.cpp:165-167 + Camera::GetRay (camera.h:58-64) ----------------
@@ -218,6 +265,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 	int path = valid ? qin.active[i] : 0;
 
 	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false;
+	int keyExtend = 0, keyMis = 0;
 
 	if (valid) {
 		uint32_t flags = ps.flags[path];
@@ -288,6 +336,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 					ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
 					ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 					emitExtend = true; skipRay = true; stayActive = true;
+					keyExtend = RayBucket(nr.D, hitPrim);
 				}
 				else {
 					const agpt_material* mat = sc.mats + prim.material;
@@ -423,6 +472,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
 									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
 									emitMis = true;
+									keyMis = RayBucket(mr.D, hitPrim);
 								}
 							}
 						}
@@ -458,6 +508,7 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 						ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 						ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
 						emitExtend = true; stayActive = true;
+						keyExtend = RayBucket(nr.D, hitPrim);
 					}
 					else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
 					else finished = true;
@@ -475,9 +526,11 @@ __global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueu
 
 	// (5) queue the next wave: one atomic per warp per queue
 	int slot = WarpAppend(emitExtend, qout.counts + 0);
-	if (emitExtend) qout.closest[slot] = path * 2;
+	if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned char)keyExtend; }
+	WarpHistAdd(emitExtend, keyExtend, qout.hist);
 	slot = WarpAppend(emitMis, qout.counts + 0);
-	if (emitMis) qout.closest[slot] = path * 2 + 1;
+	if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned char)keyMis; }
+	WarpHistAdd(emitMis, keyMis, qout.hist);
 	slot = WarpAppend(emitShadow, qout.counts + 1);
 	if (emitShadow) qout.shadow[slot] = path;
 	slot = WarpAppend(stayActive, qout.counts + 2);
