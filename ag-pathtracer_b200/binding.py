@@ -65,7 +65,8 @@ _host = None
 
 
 def lib_paths():
-    return os.path.join(_HERE, "libagpt.so"), os.path.join(_HERE, "libagpt_host.so")
+    # AGPT_LIB: experiment hook -- load an alternative build of the core library
+    return os.environ.get("AGPT_LIB") or os.path.join(_HERE, "libagpt.so"), os.path.join(_HERE, "libagpt_host.so")
 
 
 def core():

@@ -259,7 +259,10 @@ __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
 	return f3(0.f);
 }
 
-__global__ void __launch_bounds__(128) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
+#ifndef AGPT_SHADE_MIN_BLOCKS
+#define AGPT_SHADE_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool valid = i < sp.count;
 	int path = valid ? qin.active[i] : 0;
