@@ -242,6 +242,28 @@ class Context:
         return out
 
 
+def pinned_film(width, height):
+    """float32 [H, W, 4] numpy view over page-locked host memory (agpt_host_alloc); keep the
+    returned owner object alive as long as the array is used."""
+    nbytes = width * height * 16
+    p = c_void_p()
+    _check(core().agpt_host_alloc(ctypes.c_size_t(nbytes), byref(p)))
+    buf = (c_float * (width * height * 4)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.float32).reshape(height, width, 4)
+    arr[:] = 0
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                core().agpt_host_free(c_void_p(self.ptr))
+            except Exception:
+                pass
+    return arr, _Owner(p.value)
+
+
 def make_material(mtype, color, roughness=0.0, metallic=0.0):
     m = Material()
     col = (c_float * 3)(*[float(v) for v in color])

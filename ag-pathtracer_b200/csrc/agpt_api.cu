@@ -63,6 +63,7 @@ struct agpt_ctx {
 	int nMeshes = 0, nSpheres = 0, nPlanes = 0, nMats = 0;
 	agpt_camera cam;
 	bool haveCam = false;
+	float boundsLo[3] = { -1, -1, -1 }, boundsHi[3] = { 1, 1, 1 };   // bounded geometry (mesh roots), for ray bucketing only
 	int width = 0, height = 0;
 
 	// film
@@ -76,15 +77,17 @@ struct agpt_ctx {
 	DevBuf<uint32_t> u32[2];
 	DevBuf<int> queues[6];        // closest A/B (2*cap), shadow A/B, active A/B
 	DevBuf<int> sortedClosest;    // closest queue in bucket order (2*cap)
-	DevBuf<unsigned char> keys[2];
-	DevBuf<int> hist;             // 2 x AGPT_BUCKETS histogram (A/B) + offsets + running
+	DevBuf<unsigned short> keys[2], shadowKeys[2], activeKeys[2];
+	DevBuf<int> sortedShadow, sortedActive;
+	DevBuf<int> hist;             // AGPT_BUCKETS x { closest hist A/B, shadow hist A/B, offsets, running }
 	DevBuf<int> counts;           // 2 x 3
 	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned, 3 ints
 
 	agpt_stats stats;
-	bool bucketRays = true;       // bucket pass on the closest-hit queue (AGPT_BUCKET_RAYS=0 turns it off)
+	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
+	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
 
 static const size_t kMaxPathsPerBatch = (size_t)1 << 23;   // 8.4 M path slots ~ 1.8 GB of wavefront state
@@ -95,6 +98,7 @@ static DScene MakeScene(const agpt_ctx* c) {
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
 	s.width = c->width; s.height = c->height;
+	for (int a = 0; a < 3; a++) { s.cellLo[a] = c->boundsLo[a]; float e = c->boundsHi[a] - c->boundsLo[a]; s.cellScale[a] = e > 0 ? (float)(1 << AGPT_CELL_BITS) / e : 0.f; }
 	s.cam = c->cam;
 	return s;
 }
@@ -116,6 +120,8 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	for (auto& b : c->u32) CU(b.Alloc(paths));
 	CU(c->queues[0].Alloc(2 * paths)); CU(c->queues[1].Alloc(2 * paths));
 	CU(c->sortedClosest.Alloc(2 * paths)); CU(c->keys[0].Alloc(2 * paths)); CU(c->keys[1].Alloc(2 * paths));
+	CU(c->shadowKeys[0].Alloc(paths)); CU(c->shadowKeys[1].Alloc(paths)); CU(c->sortedShadow.Alloc(paths));
+	CU(c->activeKeys[0].Alloc(paths)); CU(c->activeKeys[1].Alloc(paths)); CU(c->sortedActive.Alloc(paths));
 	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths));
 	c->capacity = paths;
 	return AGPT_OK;
@@ -192,13 +198,14 @@ int agpt_create(int device, agpt_ctx** out) {
 	c->stream = c->ownStream;
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
-	CU(c->hist.Alloc(4 * AGPT_BUCKETS));
+	CU(c->hist.Alloc(8 * AGPT_BUCKETS));
 	CU(c->traceCounters.Alloc(8));
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
 	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
 	CU(cudaMallocHost((void**)&c->hostCounts, 3 * sizeof(int)));
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
+	if (const char* e = getenv("AGPT_BUCKET_ACTIVE")) c->bucketActive = atoi(e) != 0;
 	*out = c;
 	return AGPT_OK;
 }
@@ -215,6 +222,8 @@ int agpt_destroy(agpt_ctx* c) {
 	for (auto& b : c->u32) b.Free();
 	for (auto& b : c->queues) b.Free();
 	c->sortedClosest.Free(); c->keys[0].Free(); c->keys[1].Free(); c->hist.Free();
+	c->shadowKeys[0].Free(); c->shadowKeys[1].Free(); c->sortedShadow.Free();
+	c->activeKeys[0].Free(); c->activeKeys[1].Free(); c->sortedActive.Free();
 	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
 	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
@@ -268,6 +277,16 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	CU(c->meshes.Upload(table.data(), (size_t)n, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	c->nMeshes = n;
+	bool any = false;
+	for (int i = 0; i < n; i++) {
+		if (meshes[i].n_nodes == 0) continue;
+		const agpt_bvh_node& r = meshes[i].nodes[0];
+		for (int a = 0; a < 3; a++) {
+			c->boundsLo[a] = any ? (r.bmin[a] < c->boundsLo[a] ? r.bmin[a] : c->boundsLo[a]) : r.bmin[a];
+			c->boundsHi[a] = any ? (r.bmax[a] > c->boundsHi[a] ? r.bmax[a] : c->boundsHi[a]) : r.bmax[a];
+		}
+		any = true;
+	}
 	return AGPT_OK;
 }
 
@@ -379,9 +398,14 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
 		q[k].counts = c->counts.p + 3 * k;
 		q[k].keys = c->keys[k].p; q[k].hist = c->hist.p + AGPT_BUCKETS * k;
+		q[k].shadowKeys = c->shadowKeys[k].p; q[k].shadowHist = c->hist.p + AGPT_BUCKETS * (2 + k);
+		q[k].activeKeys = c->activeKeys[k].p; q[k].activeHist = c->hist.p + AGPT_BUCKETS * (4 + k);
 	}
-	int* bucketOffsets = c->hist.p + 2 * AGPT_BUCKETS;
-	int* bucketRunning = c->hist.p + 3 * AGPT_BUCKETS;
+	int* bucketOffsets = c->hist.p + 6 * AGPT_BUCKETS;
+	int* bucketRunning = c->hist.p + 7 * AGPT_BUCKETS;
+	const bool bucketActive = c->bucketActive;
+	const int* shadowQueue = q[0].shadow;
+	bool activeSorted = false;
 	const bool bucketing = c->bucketRays;
 	const int* closestQueue = q[0].closest;     // wave 0: camera rays in pixel order
 	int nClosest = n, nShadow = 0, nActive = n, cur = 0;
@@ -396,15 +420,19 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (nShadow > 0) {
-			LaunchAny(count, strictBoxes, Blocks(nShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, q[cur].shadow, nShadow, cntAny);
+			LaunchAny(count, strictBoxes, Blocks(nShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, nShadow, cntAny);
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
 		CU(cudaMemsetAsync(q[cur ^ 1].hist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+		CU(cudaMemsetAsync(q[cur ^ 1].shadowHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+		CU(cudaMemsetAsync(q[cur ^ 1].activeHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = nActive; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
-		k_shade<<<Blocks(nActive, 128), 128, 0, c->stream>>>(sc, ps, q[cur], q[cur ^ 1], sp, c->rayCounters.p);
+		WaveQueues qin = q[cur];
+		if (activeSorted) qin.active = c->sortedActive.p;
+		k_shade<<<Blocks(nActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
 		if (timing) CU(cudaEventRecord(c->evD, c->stream));
@@ -422,10 +450,24 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		closestQueue = q[cur].closest;
 		if (bucketing && nClosest > 0) {
 			// bucket pass: put rays that leave the same primitive in the same octant next to each other
-			k_bucket_scan<<<1, AGPT_BUCKETS, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
+			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
 			k_bucket_scatter<<<Blocks(nClosest, 256), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, nClosest, bucketOffsets, bucketRunning, c->sortedClosest.p);
 			c->stats.kernel_launches += 2;
 			closestQueue = c->sortedClosest.p;
+		}
+		shadowQueue = q[cur].shadow;
+		if (bucketing && nShadow > 0) {
+			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].shadowHist, bucketOffsets, bucketRunning);
+			k_bucket_scatter<<<Blocks(nShadow, 256), 256, 0, c->stream>>>(q[cur].shadow, q[cur].shadowKeys, nShadow, bucketOffsets, bucketRunning, c->sortedShadow.p);
+			c->stats.kernel_launches += 2;
+			shadowQueue = c->sortedShadow.p;
+		}
+		activeSorted = false;
+		if (bucketing && bucketActive && nActive > 0) {
+			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].activeHist, bucketOffsets, bucketRunning);
+			k_bucket_scatter<<<Blocks(nActive, 256), 256, 0, c->stream>>>(q[cur].active, q[cur].activeKeys, nActive, bucketOffsets, bucketRunning, c->sortedActive.p);
+			c->stats.kernel_launches += 2;
+			activeSorted = true;
 		}
 		c->stats.waves++;
 	}
@@ -449,7 +491,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
 	// evA/evC/evD are reused inside RunWaves when timing; the render bracket has its own pair
 	cudaEvent_t r0, r1;
 	CU(cudaEventCreate(&r0)); CU(cudaEventCreate(&r1));
@@ -506,7 +548,7 @@ int agpt_trace_primary(agpt_ctx* c, int sample, uint32_t flags, agpt_hit* out_ho
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
 	GenParams g;
 	memset(&g, 0, sizeof(g));
 	g.n = (int)wh; g.first_sample = sample; g.sample_stride = 1;
@@ -528,7 +570,7 @@ int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uin
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
 	DevBuf<float> rays;
 	DevBuf<uint32_t> seeds;
 	CU(rays.Upload(rays7, 7 * (size_t)n, c->stream));
@@ -552,7 +594,7 @@ static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, 
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
 	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
@@ -599,6 +641,18 @@ int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_sta
 	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
 	rays.Free(); seeds.Free();
 	return rcode;
+}
+
+// ---- pinned host memory for accumulators (fast H2D/D2H of the float4 film) --------------------
+int agpt_host_alloc(size_t bytes, void** out) {
+	NEED(out != nullptr && bytes > 0, AGPT_ERR_INVALID, "bad allocation request");
+	*out = nullptr;
+	CU(cudaMallocHost(out, bytes));
+	return AGPT_OK;
+}
+int agpt_host_free(void* p) {
+	if (p) CU(cudaFreeHost(p));
+	return AGPT_OK;
 }
 
 // ---- observability -----------------------------------------------------------------------

@@ -39,6 +39,7 @@ struct DScene {
 	const agpt_light* lights;
 	int n_prims, n_lights;
 	int width, height;
+	float cellLo[3], cellScale[3];   // ray-bucket grid over the bounded geometry: cell = (p - lo) * scale
 	agpt_camera cam;
 };
 

@@ -42,12 +42,19 @@ struct PathState {
 	float4* Lout;        // finished radiance per path slot
 };
 
-#define AGPT_BUCKETS 64     // ray buckets: 3 bits direction octant | 3 bits of the primitive the ray leaves
+#ifndef AGPT_CELL_BITS
+#define AGPT_CELL_BITS 3
+#endif
+#define AGPT_BUCKETS (8 << (3 * AGPT_CELL_BITS))   // ray buckets: 3 bits direction octant | 3 x AGPT_CELL_BITS bits grid cell of the ray origin
 
 struct WaveQueues {
 	int* closest;        // entries path*2 + kind (0 = path ray, 1 = MIS ray)
-	unsigned char* keys; // bucket key of each closest-queue entry
+	unsigned short* keys; // bucket key of each closest-queue entry
 	int* hist;           // AGPT_BUCKETS counters: entries per bucket
+	unsigned short* shadowKeys;
+	int* shadowHist;
+	unsigned short* activeKeys;
+	int* activeHist;
 	int* shadow;         // entries path
 	int* active;         // paths that take part in the next shade
 	int* counts;         // [0] closest, [1] shadow, [2] active
@@ -71,8 +78,16 @@ __device__ __forceinline__ int WarpAppend(bool pred, int* counter) {
 // Ray bucket: rays that leave the same primitive in the same direction octant walk similar parts
 // of the trees in the same near/far order, so putting them next to each other in the queue
 // raises both the SIMT efficiency of the lockstep walk and the L1/L2 hit rate.
-__device__ __forceinline__ int RayBucket(float3 D, int fromPrim) {
-	return (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0) | ((fromPrim & 7) << 3);
+__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D) {
+	const int hi = (1 << AGPT_CELL_BITS) - 1;
+	int cx = min(max((int)((O.x - sc.cellLo[0]) * sc.cellScale[0]), 0), hi);
+	int cy = min(max((int)((O.y - sc.cellLo[1]) * sc.cellScale[1]), 0), hi);
+	int cz = min(max((int)((O.z - sc.cellLo[2]) * sc.cellScale[2]), 0), hi);
+	// Morton-interleave the cell so neighbouring buckets are neighbouring cells
+	int cell = 0;
+#pragma unroll
+	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
+	return (cell << 3) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);
 }
 // Histogram add with one atomic per distinct key per warp.  All 32 lanes must call.
 __device__ __forceinline__ void WarpHistAdd(bool pred, int key, int* hist) {
@@ -82,22 +97,29 @@ __device__ __forceinline__ void WarpHistAdd(bool pred, int key, int* hist) {
 }
 
 // Bucket pass between shade and the next trace: exclusive scan of the histogram (one block) ...
-__global__ void k_bucket_scan(const int* hist, int* offsets, int* running) {
-	__shared__ int sh[AGPT_BUCKETS];
-	int i = threadIdx.x;
-	sh[i] = hist[i];
+__global__ void __launch_bounds__(1024) k_bucket_scan(const int* hist, int* offsets, int* running) {
+	__shared__ int warpSums[32];
+	const int PER = AGPT_BUCKETS / 1024;   // AGPT_BUCKETS is a multiple of 1024 for AGPT_CELL_BITS >= 3
+	int t = threadIdx.x;
+	int v[PER], sum = 0;
+	for (int k = 0; k < PER; k++) { v[k] = hist[t * PER + k]; sum += v[k]; }
+	// block-wide exclusive scan of `sum`
+	int lane = t & 31, w = t >> 5, x = sum;
+	for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+	if (lane == 31) warpSums[w] = x;
 	__syncthreads();
-	if (i == 0) {
-		int acc = 0;
-		for (int k = 0; k < AGPT_BUCKETS; k++) { int v = sh[k]; sh[k] = acc; acc += v; }
+	if (w == 0) {
+		int s2 = warpSums[lane];
+		for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += y; }
+		warpSums[lane] = s2;
 	}
 	__syncthreads();
-	offsets[i] = sh[i];
-	running[i] = 0;
+	int base = x - sum + (w > 0 ? warpSums[w - 1] : 0);
+	for (int k = 0; k < PER; k++) { offsets[t * PER + k] = base; running[t * PER + k] = 0; base += v[k]; }
 }
 // ... and the scatter of the queue entries into bucket order (order inside a bucket is free:
 // every path's arithmetic is independent of its queue position).
-__global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned char* __restrict__ keys, int count,
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned short* __restrict__ keys, int count,
 		const int* __restrict__ offsets, int* running, int* __restrict__ out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool valid = i < count;
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 	int path = valid ? qin.active[i] : 0;
 
 	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false;
-	int keyExtend = 0, keyMis = 0;
+	int keyExtend = 0, keyMis = 0, keyShadow = 0;
 
 	if (valid) {
 		uint32_t flags = ps.flags[path];
@@ -339,7 +361,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 					ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
 					ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 					emitExtend = true; skipRay = true; stayActive = true;
-					keyExtend = RayBucket(nr.D, hitPrim);
+					keyExtend = RayBucket(sc, nr.O, nr.D);
 				}
 				else {
 					const agpt_material* mat = sc.mats + prim.material;
@@ -456,6 +478,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 								ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
 								ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
 								emitShadow = true;
+								keyShadow = RayBucket(sc, vis.O, vis.D);
 							}
 						}
 						if (smp[0].ok) {
@@ -475,7 +498,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
 									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
 									emitMis = true;
-									keyMis = RayBucket(mr.D, hitPrim);
+									keyMis = RayBucket(sc, mr.O, mr.D);
 								}
 							}
 						}
@@ -511,7 +534,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 						ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 						ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
 						emitExtend = true; stayActive = true;
-						keyExtend = RayBucket(nr.D, hitPrim);
+						keyExtend = RayBucket(sc, nr.O, nr.D);
 					}
 					else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
 					else finished = true;
@@ -529,15 +552,18 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 
 	// (5) queue the next wave: one atomic per warp per queue
 	int slot = WarpAppend(emitExtend, qout.counts + 0);
-	if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned char)keyExtend; }
+	if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
 	WarpHistAdd(emitExtend, keyExtend, qout.hist);
 	slot = WarpAppend(emitMis, qout.counts + 0);
-	if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned char)keyMis; }
+	if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
 	WarpHistAdd(emitMis, keyMis, qout.hist);
 	slot = WarpAppend(emitShadow, qout.counts + 1);
-	if (emitShadow) qout.shadow[slot] = path;
+	if (emitShadow) { qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
+	WarpHistAdd(emitShadow, keyShadow, qout.shadowHist);
 	slot = WarpAppend(stayActive, qout.counts + 2);
-	if (stayActive) qout.active[slot] = path;
+	int keyActive = emitExtend ? keyExtend : 0;      // paths that only wait for their NEE go to bucket 0
+	if (stayActive) { qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
+	WarpHistAdd(stayActive, keyActive, qout.activeHist);
 
 	// ray statistics (warp-reduced)
 	unsigned m;

@@ -5,16 +5,23 @@
 #pragma once
 
 #include "precomp.h"
+#include "agpt.h"
 
 namespace Tmpl8 {
 
 class Accumulator {
 public:
 	Accumulator(int w, int h, const int2& scrPos = int2(0, 0)) : width(w), height(h), screenPos(scrPos), samples(0) {
-		pixels = (float3*)aligned_alloc(64, ((size_t)w * h * sizeof(float3) + 63) / 64 * 64);
+		// page-locked when a CUDA device is there (film copies at PCIe speed), plain aligned memory otherwise
+		void* p = nullptr;
+		size_t bytes = ((size_t)w * h * sizeof(float3) + 63) / 64 * 64;
+		pinned = agpt_host_alloc(bytes, &p) == AGPT_OK;
+		pixels = (float3*)(pinned ? p : aligned_alloc(64, bytes));
 		Clear();
 	}
-	~Accumulator() { free(pixels); }
+	// wrap caller-owned film memory (not freed here)
+	Accumulator(int w, int h, float3* external) : width(w), height(h), screenPos(0, 0), pixels(external), samples(0), pinned(false), owned(false) {}
+	~Accumulator() { if (owned) { if (pinned) agpt_host_free(pixels); else free(pixels); } }
 	Accumulator(const Accumulator&) = delete;
 	Accumulator& operator=(const Accumulator&) = delete;
 
@@ -38,6 +45,7 @@ private:
 	int2 screenPos;
 	float3* pixels;
 	int samples;
+	bool pinned = false, owned = true;
 };
 
 } // namespace Tmpl8

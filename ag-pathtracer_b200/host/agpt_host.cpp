@@ -205,10 +205,8 @@ int agpt_host_tracer_render(agpt_host_tracer* t, agpt_host_scene* s, int width, 
 	g_hostError.clear();
 	HOST_TRY(
 		if (reupload) t->tracer->Upload(s->scene);
-		Accumulator acc(width, height);
-		memcpy(acc.Pixels(), host_rgba, (size_t)width * height * sizeof(float3));
+		Accumulator acc(width, height, reinterpret_cast<float3*>(host_rgba));     // the caller's film, in place
 		t->tracer->Render(s->scene, *s->camera, acc, first_sample, num_samples, depth_arg, flags);
-		memcpy(host_rgba, acc.Pixels(), (size_t)width * height * sizeof(float3));
 	)
 	return AGPT_OK;
 }

@@ -267,7 +267,7 @@ def main():
 
     # ---- end-to-end through the reference-facing host API (host buffers in and out) -------
     tracer = pkg.HostTracer(depth, local_rank)
-    host_acc = np.zeros((H, W, 4), np.float32)
+    host_acc, _film_owner = pkg.pinned_film(W, H)          # page-locked host film, as the host mirror's Accumulator allocates it
     tracer.render(scene, W, H, host_acc, 0, 1, depth_arg)             # uploads the scene, warms up
     e2e_steps = max(1, min(args.steps, 3))
     tctx_stats0 = None

@@ -18,6 +18,7 @@
 #ifndef AGPT_H
 #define AGPT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -222,6 +223,11 @@ int agpt_read_accum(agpt_ctx* ctx, float* host_rgba);           /* D2H of float4
 int agpt_write_accum(agpt_ctx* ctx, const float* host_rgba);    /* H2D (resume) */
 /* Accumulator::CopyToSurface (myapp.h:34-41): /samples, pow(1/2.2), 8-bit pack 0x00RRGGBB. */
 int agpt_resolve(agpt_ctx* ctx, int samples, uint32_t* host_rgb8);
+
+/* Page-locked host memory for accumulator buffers (what MALLOC64 is upstream, myapp.h:11):
+ * agpt_read_accum / agpt_write_accum on such a buffer run at PCIe speed. */
+int agpt_host_alloc(size_t bytes, void** out);
+int agpt_host_free(void* p);
 
 /* ---- observability ------------------------------------------------------------------- */
 
