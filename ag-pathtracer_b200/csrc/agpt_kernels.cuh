@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 
 // ---- trace kernels ---------------------------------------------------------------------
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, int count,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_closest(DScene sc,
 }
 
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, int count,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;

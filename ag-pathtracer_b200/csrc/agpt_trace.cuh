@@ -16,7 +16,12 @@
 
 #include "agpt_device.cuh"
 
+#ifndef AGPT_STACK_SMEM
 #define AGPT_STACK_SMEM 24      // stack entries per thread kept in shared memory
+#endif
+#ifndef AGPT_TRACE_MIN_BLOCKS
+#define AGPT_TRACE_MIN_BLOCKS 1
+#endif
 #define AGPT_STACK_LOCAL 40     // overflow entries in local memory (SAH trees here are <= ~30 deep)
 #define AGPT_TRACE_THREADS 128
 

@@ -209,6 +209,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg = load_pkg()
@@ -309,7 +311,9 @@ def main():
                      "ms_other": tm.ms_other, "waves": tm.waves, "rays_per_path": cn.rays / max(cn.paths, 1)}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as f:
-                roofline["traffic"] = json.load(f).get("k_trace_closest_dram_bytes_per_launch")
+                per_ray = json.load(f).get("k_trace_closest_dram_bytes_per_ray")
+                # ncu --set full capture (profiles/), scaled to this run's average launch
+                roofline["traffic"] = per_ray * rays_closest / max(cn.launches_closest, 1) if per_ray else None
         except Exception:
             pass
 
