@@ -316,7 +316,7 @@ class HostScene:
 
     def tables(self):
         """agpt_scene_tables view (opaque bytes) of the flattened scene, valid while the scene lives."""
-        buf = ctypes.create_string_buffer(6 * 16 + 19 * 4 + 4)
+        buf = ctypes.create_string_buffer(6 * 16 + 19 * 4 + 4 + 40 + 16)
         _check(host().agpt_host_scene_tables(self._h, buf), host_side=True)
         return buf
 

@@ -58,6 +58,9 @@ struct agpt_ctx {
 	DevBuf<agpt_prim> prims;
 	DevBuf<agpt_material> mats;
 	DevBuf<agpt_light> lights;
+	DevBuf<float> envRgb, envFunc, envCdf;
+	float envFuncInt = 0;
+	int envW = 0, envH = 0;
 	std::vector<agpt_prim> hostPrims;
 	std::vector<agpt_light> hostLights;
 	int nMeshes = 0, nSpheres = 0, nPlanes = 0, nMats = 0;
@@ -97,6 +100,7 @@ static DScene MakeScene(const agpt_ctx* c) {
 	s.prims = c->prims.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
+	s.envRgb = c->envRgb.p; s.envFunc = c->envFunc.p; s.envCdf = c->envCdf.p; s.envFuncInt = c->envFuncInt; s.envW = c->envW; s.envH = c->envH;
 	s.width = c->width; s.height = c->height;
 	for (int a = 0; a < 3; a++) { s.cellLo[a] = c->boundsLo[a]; float e = c->boundsHi[a] - c->boundsLo[a]; s.cellScale[a] = e > 0 ? (float)(1 << AGPT_CELL_BITS) / e : 0.f; }
 	s.cam = c->cam;
@@ -142,6 +146,8 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 		NEED(p.material < c->nMats, AGPT_ERR_INVALID, "primitive row points outside the material table");
 		NEED(p.area_light < (int)c->hostLights.size(), AGPT_ERR_INVALID, "primitive row points outside the light table");
 	}
+	for (auto& l : c->hostLights)
+		NEED(l.type != AGPT_LIGHT_INFINITE_AREA || c->envW > 0, AGPT_ERR_STATE, "InfiniteAreaLight without an environment map (agpt_upload_envmap)");
 	for (auto& l : c->hostLights)
 		NEED(l.type != AGPT_LIGHT_AREA || (l.prim >= 0 && l.prim < (int)c->hostPrims.size()), AGPT_ERR_INVALID, "area light without a primitive");
 	return AGPT_OK;
@@ -217,6 +223,7 @@ int agpt_destroy(agpt_ctx* c) {
 	for (auto& m : c->meshStore) m.Free();
 	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free();
+	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
 	for (auto& b : c->i32) b.Free();
 	for (auto& b : c->u32) b.Free();
@@ -306,6 +313,23 @@ SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n)
 SIMPLE_UPLOAD(agpt_upload_lights, agpt_light, lights, c->hostLights.assign(rows, rows + n))
 SIMPLE_UPLOAD(agpt_upload_primitives, agpt_prim, prims, c->hostPrims.assign(rows, rows + n))
 
+int agpt_upload_envmap(agpt_ctx* c, const agpt_envmap* env) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
+	c->envW = c->envH = 0; c->envFuncInt = 0;
+	if (!env || env->width == 0) return AGPT_OK;
+	NEED(env->width > 0 && env->height > 0 && env->rgb && env->func && env->cdf, AGPT_ERR_INVALID, "bad environment map");
+	size_t n = (size_t)env->width * env->height;
+	CU(c->envRgb.Upload(env->rgb, 3 * n, c->stream));
+	CU(c->envFunc.Upload(env->func, n, c->stream));
+	CU(c->envCdf.Upload(env->cdf, n + 1, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->envW = env->width; c->envH = env->height; c->envFuncInt = env->func_int;
+	return AGPT_OK;
+}
+
 int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
 	NEED(c != nullptr && cam != nullptr, AGPT_ERR_INVALID, "null camera");
 	c->cam = *cam;
@@ -330,7 +354,7 @@ int agpt_set_film(agpt_ctx* c, int width, int height) {
 
 int agpt_scene_bytes(agpt_ctx* c, uint64_t* out) {
 	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
-	uint64_t b = c->meshes.Bytes() + c->spheres.Bytes() + c->planes.Bytes() + c->prims.Bytes() + c->mats.Bytes() + c->lights.Bytes();
+	uint64_t b = c->envRgb.Bytes() + c->envFunc.Bytes() + c->envCdf.Bytes() + c->meshes.Bytes() + c->spheres.Bytes() + c->planes.Bytes() + c->prims.Bytes() + c->mats.Bytes() + c->lights.Bytes();
 	for (auto& m : c->meshStore) b += m.nodes.Bytes() + m.tris.Bytes() + m.normals.Bytes() + m.uvs.Bytes() + m.ids.Bytes();
 	*out = b;
 	return AGPT_OK;

@@ -409,6 +409,68 @@ __device__ __forceinline__ float SpherePdfFrom(const agpt_sphere& sp, float3 ref
 	return UniformConePdf(cosThetaMax);
 }
 
+// ---------------------------------------------------------------------------------------
+// InfiniteAreaLight (lights.cpp:31-112, built with ILS), HDRTexture::value (texture.h:59-67),
+// Distribution1D::SampleContinuous / DiscretePDF (sampling.h:4-18,38-64)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float SphericalTheta(float3 v) { return racos(rclamp(v.z, -1.f, 1.f)); }                 // common.h:158-160
+__device__ __forceinline__ float SphericalPhi(float3 v) { float p = ratan2(v.y, v.x); return (p < 0) ? (p + AGPT_TWOPI) : p; }   // common.h:162-165
+__device__ __forceinline__ int EnvMod(int a, int b) { int r = a - (a / b) * b; return r < 0 ? r + b : r; }           // texture.h:78-81
+__device__ __forceinline__ float3 EnvTexel(const DScene& sc, int x, int y) {
+	const float* p = sc.envRgb + 3 * ((size_t)y * sc.envW + x);
+	return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+// InfiniteAreaLight::Le(ray): direction -> lat-long texel, nearest lookup with wrap (lights.cpp:108-112)
+__device__ __noinline__ float3 EnvLe(const DScene& sc, float3 rayD) {
+	float3 w = normalize(rayD);
+	w = f3(w.x, w.z, w.y);
+	float u = SphericalPhi(w) * AGPT_INV2PI, v = SphericalTheta(w) * AGPT_INVPI;
+	int s = (int)floorf(u * sc.envW - .5f);
+	int t = (int)floorf(v * sc.envH - .5f);
+	return EnvTexel(sc, EnvMod(s, sc.envW), EnvMod(t, sc.envH));
+}
+// InfiniteAreaLight::Pdf_Li (lights.cpp:92-106)
+__device__ __noinline__ float EnvPdfLi(const DScene& sc, float3 wi) {
+	float3 w = normalize(wi);
+	w = f3(w.x, w.z, w.y);
+	float theta = SphericalTheta(w), phi = SphericalPhi(w);
+	float sinTheta = rsin(theta);
+	if (sinTheta == 0) return 0;
+	int x = min(max((int)(phi * AGPT_INV2PI * sc.envW), 0), sc.envW - 1);
+	int y = min(max((int)(theta * AGPT_INVPI * sc.envH), 0), sc.envH - 1);
+	int count = sc.envW * sc.envH;
+	float discrete = __ldg(sc.envFunc + (y * sc.envW + x)) / (sc.envFuncInt * count);
+	return count * discrete / (2 * AGPT_PI * AGPT_PI * sinTheta);
+}
+// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): u01 is the one extra draw it makes.
+// Returns false where upstream returns black before writing *pdf (mapPdf == 0).
+__device__ __noinline__ bool EnvSampleLi(const DScene& sc, float u01, float3* wi, float* pdf) {
+	const int n = sc.envW * sc.envH;
+	// FindInterval(cdf.size(), cdf[index] <= u) (sampling.h:4-18)
+	int first = 0, len = n + 1;
+	while (len > 0) {
+		int half = len >> 1, middle = first + half;
+		if (__ldg(sc.envCdf + middle) <= u01) { first = middle + 1; len -= half + 1; }
+		else len = half;
+	}
+	int offset = min(max(first - 1, 0), n + 1 - 2);
+	float c0 = __ldg(sc.envCdf + offset), c1 = __ldg(sc.envCdf + offset + 1);
+	float du = u01 - c0;
+	if ((c1 - c0) > 0) du /= c1 - c0;
+	float mapPdf = (sc.envFuncInt > 0) ? __ldg(sc.envFunc + offset) / sc.envFuncInt : 0;
+	float sample = (offset + du) / n;
+	if (mapPdf == 0) return false;
+	int idx = (int)(sample * n);
+	float uvx = ((idx % sc.envW) + .5f) / sc.envW, uvy = ((idx / sc.envW) + .5f) / sc.envH;
+	float theta = uvy * AGPT_PI, phi = uvx * AGPT_TWOPI;
+	float cosTheta = rcos(theta), sinTheta = rsin(theta);
+	float sinPhi = rsin(phi), cosPhi = rcos(phi);
+	*wi = f3(sinTheta * cosPhi, cosTheta, sinTheta * sinPhi);
+	*pdf = mapPdf / (2 * AGPT_PI * AGPT_PI * sinTheta);
+	if (sinTheta == 0) *pdf = 0;
+	return true;
+}
+
 __device__ __forceinline__ float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {   // integrator.h:33-36
 	float f = nf * fPdf, g = ng * gPdf;
 	return (f * f) / (f * f + g * g);

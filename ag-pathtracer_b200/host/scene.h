@@ -25,6 +25,7 @@ struct FlatScene {
 	std::vector<agpt_light> lights;
 	std::vector<agpt_mesh_desc> meshes;
 	std::vector<FlatTriangles> meshTris;
+	agpt_envmap envmap = { 0, 0, nullptr, nullptr, nullptr, 0.f };   // borrowed from the scene's InfiniteAreaLight
 	uint64_t Bytes() const {
 		uint64_t b = prims.size() * sizeof(agpt_prim) + spheres.size() * sizeof(agpt_sphere) + planes.size() * sizeof(agpt_plane)
 			+ materials.size() * sizeof(agpt_material) + lights.size() * sizeof(agpt_light);
@@ -113,6 +114,7 @@ public:
 				auto it = primIndex.find(static_cast<const AreaLight*>(l.get())->Shape.get());
 				if (it != primIndex.end()) rec.prim = it->second;
 			}
+			if (rec.type == AGPT_LIGHT_INFINITE_AREA) flat->envmap = static_cast<const InfiniteAreaLight*>(l.get())->Export();
 			float3 e = l->Emission();
 			rec.lemit[0] = e.x; rec.lemit[1] = e.y; rec.lemit[2] = e.z;
 			flat->lights.push_back(rec);

@@ -15,7 +15,10 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
+#include <string>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -316,6 +319,64 @@ inline void BuildConfig6(Scene* scene, int level) {
 	scene->camera.aperture = .1f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Procedural environment map.  The reference's default lighting is an HDR file that is not in
+// its repo (small_workshop_1k.hdr, myapp.cpp:113); this writes a deterministic stand-in --
+// gradient sky, warm horizon band, ground, a small very bright sun -- as a flat (non-RLE)
+// Radiance RGBE file that both stb_image (oracle) and host/texture.h read.
+// ---------------------------------------------------------------------------------------
+inline std::string EnvMapPath() {
+	const char* dir = std::getenv("AGPT_TMPDIR");
+	return std::string(dir ? dir : "/tmp") + "/agpt_procedural_sky_1k.hdr";
+}
+inline void WriteProceduralHdr(const std::string& path, int W = 1024, int H = 512) {
+	std::vector<unsigned char> bytes((size_t)W * H * 4);
+	for (int y = 0; y < H; y++)
+		for (int x = 0; x < W; x++) {
+			float v = (y + .5f) / H, u = (x + .5f) / W;           // v = 0: zenith, v = 1: nadir
+			float up = 1.f - 2.f * v;                              // ~cos(theta)
+			float rgb[3];
+			if (up > 0) { rgb[0] = .25f + .35f * (1 - up); rgb[1] = .4f + .3f * (1 - up); rgb[2] = .9f - .2f * (1 - up); }
+			else { rgb[0] = .22f; rgb[1] = .2f; rgb[2] = .17f; }
+			float band = 1.f - std::fabs(up) * 8.f;
+			if (band > 0) { rgb[0] += .5f * band; rgb[1] += .35f * band; rgb[2] += .15f * band; }
+			float du = (u - .62f) * 2.f, dv = v - .28f;
+			if (du * du + dv * dv < .0002f) { rgb[0] = 120.f; rgb[1] = 108.f; rgb[2] = 90.f; }   // the sun
+			float m = std::max(rgb[0], std::max(rgb[1], rgb[2]));
+			unsigned char* p = &bytes[4 * ((size_t)y * W + x)];
+			if (m < 1e-32f) { p[0] = p[1] = p[2] = p[3] = 0; continue; }
+			int e;
+			float scale = std::frexp(m, &e) * 256.f / m;
+			p[0] = (unsigned char)(rgb[0] * scale); p[1] = (unsigned char)(rgb[1] * scale); p[2] = (unsigned char)(rgb[2] * scale);
+			p[3] = (unsigned char)(e + 128);
+		}
+	FILE* f = std::fopen(path.c_str(), "wb");
+	if (!f) return;
+	std::fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", H, W);
+	std::fwrite(bytes.data(), 1, bytes.size(), f);
+	std::fclose(f);
+}
+
+// cfg 7: the reference's own default scene, SimpleTestScene (myapp.cpp:55-114):
+// backdrop mesh + one gold Disney sphere, thin-lens camera (aperture .1), lit only by an
+// InfiniteAreaLight -- with the procedural map standing in for the missing asset.
+inline void BuildConfig7(Scene* scene) {
+	float roughness = .5f;
+	auto gold = DisneyMaterial::Make((float3(0.944f, 0.776f, 0.373f)), roughness, 1.f);
+	auto floor = DisneyMaterial::Make(hex2lin(0xcbceb1), 1.f, 0.f);
+	auto backdrop = TriangleMesh::CreateBackdrop(make_float3(0, -1, 20), float3(40, 20, 40), 7.5, 32, floor);
+	scene->primitives.push_back(std::make_shared<BVHTriMesh>(backdrop, floor, 1));
+	scene->primitives.push_back(std::make_shared<Sphere>(float3(0, 0, 0), 1.f, gold));
+	scene->camera.lookfrom = float3(-1.46, 1.16, -4.64);
+	scene->camera.lookat = float3(0, 0, 0);
+	scene->camera.vup = float3(0, 1, 0);
+	scene->camera.aspect_ratio = 1;
+	scene->camera.aperture = .1f;
+	std::string path = EnvMapPath();
+	WriteProceduralHdr(path);
+	scene->lights.push_back(std::make_shared<InfiniteAreaLight>(path));
+}
+
 // level <= 0 selects the BASELINE.json size of each configuration.
 inline bool BuildConfig(Scene* scene, int config, int level) {
 	switch (config) {
@@ -325,6 +386,7 @@ inline bool BuildConfig(Scene* scene, int config, int level) {
 	case 4: BuildConfig4(scene, level > 0 ? level : 8); return true;
 	case 5: BuildConfig5(scene, level > 0 ? level : 7); return true;
 	case 6: BuildConfig6(scene, level > 0 ? level : 2); return true;
+	case 7: BuildConfig7(scene); return true;
 	default: return false;
 	}
 }

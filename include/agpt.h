@@ -105,7 +105,7 @@ typedef struct agpt_material {
 	float alpha_y;
 } agpt_material;
 
-enum { AGPT_LIGHT_AREA = 0, AGPT_LIGHT_UNIFORM_INFINITE = 1 };
+enum { AGPT_LIGHT_AREA = 0, AGPT_LIGHT_UNIFORM_INFINITE = 1, AGPT_LIGHT_INFINITE_AREA = 2 };
 
 /* Scene::lights in list order (lights.h:37-51,72-87). */
 typedef struct agpt_light {
@@ -115,6 +115,17 @@ typedef struct agpt_light {
 	float lemit[3];
 	float pad2;
 } agpt_light;
+
+/* InfiniteAreaLight (lights.h:52-70, lights.cpp:31-112): lat-long HDR map (HDRTexture,
+ * texture.h:41-84) plus the piecewise-constant distribution over its texels (Distribution1D,
+ * sampling.h:20-69) that the light's constructor builds (lights.cpp:33-47).  One per scene. */
+typedef struct agpt_envmap {
+	int32_t width, height;
+	const float* rgb;        /* width*height x 3 floats, row-major, as stbi_loadf decodes the .hdr */
+	const float* func;       /* width*height: max(r,g,b) * sin(theta_row) */
+	const float* cdf;        /* width*height + 1 */
+	float func_int;          /* Distribution1D::funcInt */
+} agpt_envmap;
 
 /* Derived camera vectors exactly as Camera::updateCoords leaves them (camera.h:77-90);
  * computed on the host (tan, double->float), the device only adds and multiplies. */
@@ -183,6 +194,7 @@ int agpt_upload_planes(agpt_ctx* ctx, const agpt_plane* planes, int n);
 int agpt_upload_primitives(agpt_ctx* ctx, const agpt_prim* prims, int n);
 int agpt_upload_materials(agpt_ctx* ctx, const agpt_material* materials, int n);
 int agpt_upload_lights(agpt_ctx* ctx, const agpt_light* lights, int n);
+int agpt_upload_envmap(agpt_ctx* ctx, const agpt_envmap* env);          /* NULL clears it */
 int agpt_set_camera(agpt_ctx* ctx, const agpt_camera* camera);          /* Camera, camera.h:38-56 */
 int agpt_set_film(agpt_ctx* ctx, int width, int height);                /* Accumulator(w,h), myapp.h:10-13 */
 int agpt_scene_bytes(agpt_ctx* ctx, uint64_t* out);                     /* resident scene bytes in HBM */

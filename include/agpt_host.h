@@ -45,6 +45,7 @@ typedef struct agpt_scene_tables {
 	const agpt_material* materials; int n_materials;
 	const agpt_light* lights; int n_lights;
 	agpt_camera camera;
+	agpt_envmap envmap;      /* width == 0: none */
 } agpt_scene_tables;
 int agpt_host_scene_tables(agpt_host_scene* scene, agpt_scene_tables* out);
 

@@ -91,6 +91,10 @@ struct OScene {
 	std::vector<agpt_material> mats;
 	std::vector<agpt_light> lights;
 	agpt_camera cam;
+	// InfiniteAreaLight tables (lights.cpp:31-48, texture.h:41-57, sampling.h:22-35)
+	int envW = 0, envH = 0;
+	std::vector<float> envRgb, envFunc, envCdf;
+	float envFuncInt = 0;
 };
 
 struct Ray {                       // camera.h:3-15
@@ -625,6 +629,56 @@ float SpherePdf(const agpt_sphere& sp, V3 refP) {                               
 	return 1 / (2 * kPi * (1 - cosThetaMax));
 }
 
+// ---- InfiniteAreaLight (lights.cpp:50-112, ILS), HDRTexture::value (texture.h:59-81), Distribution1D (sampling.h)
+inline float SphericalTheta(V3 v) { return std::acos(tclamp(v.z, -1.f, 1.f)); }                        // common.h:158-160
+inline float SphericalPhi(V3 v) { float p = std::atan2(v.y, v.x); return (p < 0) ? (p + kTwoPi) : p; }   // common.h:162-165
+inline int EnvMod(int a, int b) { int r = a - (a / b) * b; return (r < 0) ? r + b : r; }
+V3 EnvLe(const OScene& sc, V3 rayD) {
+	V3 w = normalize(rayD);
+	w = v3(w.x, w.z, w.y);
+	float u = SphericalPhi(w) * kInv2Pi, v = SphericalTheta(w) * kInvPi;
+	int s = (int)std::floor(u * sc.envW - .5f);
+	int t = (int)std::floor(v * sc.envH - .5f);
+	int x = EnvMod(s, sc.envW), y = EnvMod(t, sc.envH);
+	return v3(&sc.envRgb[3 * ((size_t)y * sc.envW + x)]);
+}
+float EnvPdfLi(const OScene& sc, V3 wi) {
+	V3 w = normalize(wi);
+	w = v3(w.x, w.z, w.y);
+	float theta = SphericalTheta(w), phi = SphericalPhi(w);
+	float sinTheta = std::sin(theta);
+	if (sinTheta == 0) return 0;
+	int x = std::min(std::max(int(phi * kInv2Pi * sc.envW), 0), sc.envW - 1);
+	int y = std::min(std::max(int(theta * kInvPi * sc.envH), 0), sc.envH - 1);
+	int count = sc.envW * sc.envH;
+	float discrete = sc.envFunc[y * sc.envW + x] / (sc.envFuncInt * count);
+	return count * discrete / (2 * kPi * kPi * sinTheta);
+}
+bool EnvSampleLi(const OScene& sc, float u, V3* wi, float* pdf) {
+	const int n = sc.envW * sc.envH;
+	int first = 0, len = n + 1;                                                           // FindInterval (sampling.h:4-18)
+	while (len > 0) {
+		int half = len >> 1, middle = first + half;
+		if (sc.envCdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+		else len = half;
+	}
+	int offset = std::min(std::max(first - 1, 0), n + 1 - 2);
+	float du = u - sc.envCdf[offset];
+	if ((sc.envCdf[offset + 1] - sc.envCdf[offset]) > 0) du /= sc.envCdf[offset + 1] - sc.envCdf[offset];
+	float mapPdf = (sc.envFuncInt > 0) ? sc.envFunc[offset] / sc.envFuncInt : 0;
+	float sample = (offset + du) / n;
+	if (mapPdf == 0) return false;
+	int idx = int(sample * n);
+	float uvx = ((idx % sc.envW) + .5f) / sc.envW, uvy = ((idx / sc.envW) + .5f) / sc.envH;
+	float theta = uvy * kPi, phi = uvx * kTwoPi;
+	float cosTheta = std::cos(theta), sinTheta = std::sin(theta);
+	float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+	*wi = v3(sinTheta * cosPhi, cosTheta, sinTheta * sinPhi);
+	*pdf = mapPdf / (2 * kPi * kPi * sinTheta);
+	if (sinTheta == 0) *pdf = 0;
+	return true;
+}
+
 inline float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) { float f = nf * fPdf, g = ng * gPdf; return (f * f) / (f * f + g * g); }   // integrator.h:33-36
 
 // EstimateDirect (integrator.h:38-93)
@@ -649,6 +703,13 @@ V3 EstimateDirect(const OScene& sc, const Surface& si, const Bsdf& bsdf, V3 wo, 
 				vis = Ray(si.p + kEps * wi, wi, dist - 10 * kEps);
 				Li = lemit;
 			}
+		}
+	}
+	else if (light.type == AGPT_LIGHT_INFINITE_AREA) {                                    // lights.cpp:50-90
+		float u01 = rng.Float();
+		if (EnvSampleLi(sc, u01, &wi, &lightPdf)) {
+			vis = Ray(si.p + kEps * si.n, wi);
+			Li = EnvLe(sc, vis.D);
 		}
 	}
 	else {                                                                                // lights.cpp:15-24, common.h:73-97
@@ -682,6 +743,7 @@ V3 EstimateDirect(const OScene& sc, const Surface& si, const Bsdf& bsdf, V3 wo, 
 				const agpt_prim& lpr = sc.prims[light.prim];
 				lp = lpr.type == AGPT_PRIM_SPHERE ? SpherePdf(sc.spheres[lpr.payload], si.p) : 0.f;
 			}
+			else if (light.type == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wi);
 			else lp = dot(si.n, wi) > 0 ? kInv2Pi : 0.f;                                  // lights.cpp:26-28
 			if (lp == 0) return Ld;
 			float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
@@ -691,6 +753,7 @@ V3 EstimateDirect(const OScene& sc, const Surface& si, const Bsdf& bsdf, V3 wo, 
 			V3 Lr = v3(0.f);
 			if (found) { if (sc.prims[h.prim].area_light == lightIdx) Lr = lemit; }
 			else if (light.type == AGPT_LIGHT_UNIFORM_INFINITE) Lr = lemit;
+			else if (light.type == AGPT_LIGHT_INFINITE_AREA) Lr = EnvLe(sc, ray.D);
 			if (!IsBlack(Lr)) Ld += f * Lr * weight / scatteringPdf;
 		}
 	}
@@ -710,7 +773,10 @@ V3 Li(const OScene& sc, Ray ray, int maxDepth, int depthArg, Rng& rng, Counters&
 				L += beta * (al >= 0 ? v3(sc.lights[al].lemit) : v3(0.f));
 			}
 			else {
-				for (auto& l : sc.lights) if (l.type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * v3(l.lemit);
+				for (auto& l : sc.lights) {
+					if (l.type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * v3(l.lemit);
+					else if (l.type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, ray.D);
+				}
 			}
 		}
 		if (!found || bounces >= maxDepth) break;
@@ -794,6 +860,7 @@ struct agpt_oracle_tables {            // what tests pass in: the flattened tabl
 	const agpt_material* materials; int n_materials;
 	const agpt_light* lights; int n_lights;
 	agpt_camera camera;
+	agpt_envmap envmap;
 };
 
 void* agpt_oracle_scene_create(const agpt_oracle_tables* t) {
@@ -804,6 +871,13 @@ void* agpt_oracle_scene_create(const agpt_oracle_tables* t) {
 	s->mats.assign(t->materials, t->materials + t->n_materials);
 	s->lights.assign(t->lights, t->lights + t->n_lights);
 	s->cam = t->camera;
+	if (t->envmap.width > 0) {
+		size_t n = (size_t)t->envmap.width * t->envmap.height;
+		s->envW = t->envmap.width; s->envH = t->envmap.height; s->envFuncInt = t->envmap.func_int;
+		s->envRgb.assign(t->envmap.rgb, t->envmap.rgb + 3 * n);
+		s->envFunc.assign(t->envmap.func, t->envmap.func + n);
+		s->envCdf.assign(t->envmap.cdf, t->envmap.cdf + n + 1);
+	}
 	for (int i = 0; i < t->n_meshes; i++) {
 		const agpt_mesh_desc& d = t->meshes[i];
 		Mesh m;

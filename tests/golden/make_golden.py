@@ -19,8 +19,8 @@ from oracle import ref_binding as ref  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 # (config, icosphere level, W, H, spp) -- small enough to commit, every code path covered
-CASES = [(1, 0, 64, 36, 4), (2, 3, 64, 36, 2), (3, 2, 64, 36, 2), (4, 2, 64, 36, 2), (5, 2, 64, 36, 2), (6, 2, 64, 36, 4)]
-DEFAULTS = {1: (5, 0), 2: (1, 0), 3: (8, 0), 4: (8, 0), 5: (16, 4), 6: (5, 0)}   # max_depth, depth_arg (config_scenes.h)
+CASES = [(1, 0, 64, 36, 4), (2, 3, 64, 36, 2), (3, 2, 64, 36, 2), (4, 2, 64, 36, 2), (5, 2, 64, 36, 2), (6, 2, 64, 36, 4), (7, 0, 48, 48, 4)]
+DEFAULTS = {1: (5, 0), 2: (1, 0), 3: (8, 0), 4: (8, 0), 5: (16, 4), 6: (5, 0), 7: (5, 0)}   # max_depth, depth_arg (config_scenes.h)
 
 
 def sha(a):

@@ -18,7 +18,7 @@ def rel_rmse(gpu, cpu):
     return float(np.sqrt(np.mean((g - c) ** 2)) / max(np.mean(np.abs(c)), 1e-30))
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7])
 def test_against_golden(agpt, gpu_ctx, cfg):
     g = np.load(os.path.join(GOLDEN, f"scene_cfg{cfg}.npz"))
     _, level, W, H, spp, md, da = [int(v) for v in g["case"]]
