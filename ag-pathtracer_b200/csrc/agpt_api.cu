@@ -86,9 +86,13 @@ struct agpt_ctx {
 	DevBuf<int> counts;           // 2 x 3
 	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
 	DevBuf<RayCounters> rayCounters;
-	int* hostCounts = nullptr;    // pinned, 3 ints
+	int* hostCounts = nullptr;    // pinned ring of kRing x 3 ints
+	cudaEvent_t ringEvents[8] = {};
 
 	agpt_stats stats;
+	bool asyncWaves = false;      // AGPT_ASYNC_WAVES=1: run one wave ahead of the landed queue counts instead of syncing
+	                              // every wave.  Measured slower (N=1: 133 vs 130.5 ms/step, N=8: 142.8 vs 139.3): the loose
+	                              // launch bounds and the extra empty wave cost more than the ~30 us sync gaps they remove.
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
@@ -122,11 +126,12 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	for (auto& b : c->f4) CU(b.Alloc(paths));
 	for (auto& b : c->i32) CU(b.Alloc(paths));
 	for (auto& b : c->u32) CU(b.Alloc(paths));
-	CU(c->queues[0].Alloc(2 * paths)); CU(c->queues[1].Alloc(2 * paths));
-	CU(c->sortedClosest.Alloc(2 * paths)); CU(c->keys[0].Alloc(2 * paths)); CU(c->keys[1].Alloc(2 * paths));
-	CU(c->shadowKeys[0].Alloc(paths)); CU(c->shadowKeys[1].Alloc(paths)); CU(c->sortedShadow.Alloc(paths));
-	CU(c->activeKeys[0].Alloc(paths)); CU(c->activeKeys[1].Alloc(paths)); CU(c->sortedActive.Alloc(paths));
-	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths));
+	const size_t slack = 1024;       // kernels read queue[i] before they know the queue length (i < grid * block)
+	CU(c->queues[0].Alloc(2 * paths + slack)); CU(c->queues[1].Alloc(2 * paths + slack));
+	CU(c->sortedClosest.Alloc(2 * paths + slack)); CU(c->keys[0].Alloc(2 * paths + slack)); CU(c->keys[1].Alloc(2 * paths + slack));
+	CU(c->shadowKeys[0].Alloc(paths + slack)); CU(c->shadowKeys[1].Alloc(paths + slack)); CU(c->sortedShadow.Alloc(paths + slack));
+	CU(c->activeKeys[0].Alloc(paths + slack)); CU(c->activeKeys[1].Alloc(paths + slack)); CU(c->sortedActive.Alloc(paths + slack));
+	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths + slack));
 	c->capacity = paths;
 	return AGPT_OK;
 }
@@ -156,11 +161,11 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // ---- launch helpers: template flags from run-time flags --------------------------------------
-static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, int n, unsigned long long* cnt) {
+static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt) {
 	if (count) { if (strictBoxes) k_trace_closest<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
 	else { if (strictBoxes) k_trace_closest<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
 }
-static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, int n, unsigned long long* cnt) {
+static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt) {
 	if (count) { if (strictBoxes) k_trace_any<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
 	else { if (strictBoxes) k_trace_any<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
 }
@@ -209,7 +214,9 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
 	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
-	CU(cudaMallocHost((void**)&c->hostCounts, 3 * sizeof(int)));
+	CU(cudaMallocHost((void**)&c->hostCounts, 8 * 3 * sizeof(int)));
+	for (auto& e : c->ringEvents) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_ACTIVE")) c->bucketActive = atoi(e) != 0;
 	*out = c;
@@ -233,6 +240,7 @@ int agpt_destroy(agpt_ctx* c) {
 	c->activeKeys[0].Free(); c->activeKeys[1].Free(); c->sortedActive.Free();
 	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
+	for (auto& e : c->ringEvents) if (e) cudaEventDestroy(e);
 	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
 	cudaStreamDestroy(c->ownStream);
 	delete c;
@@ -414,7 +422,16 @@ int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
 }
 
 // ---- the wave loop -------------------------------------------------------------------------
-// Runs `n` already-generated paths (slots 0..n-1, queues A filled by k_generate) to completion.
+// Runs `n` already-generated paths (slots 0..n-1, queues A and counts A filled by k_generate) to
+// completion.  Queue lengths stay on the device (kernels read them); the host sizes grids from
+// upper bounds.  Default: after every wave the host waits for that wave's three counts (one
+// 12-byte copy to pinned memory), so the bounds are exact and the loop ends with the wave that
+// empties the active list.  Optional (asyncWaves): the host runs up to kMaxAhead waves ahead of
+// the newest landed counts, tightening bounds as copies land (the active list only shrinks: a
+// later wave has at most `active` paths, 2*active closest-hit rays and `active` shadow rays);
+// empty waves launched past the end are no-ops.  AGPT_FLAG_TIMING brackets the kernel classes
+// of every wave with events.
+static const int kMaxAhead = 2, kRing = 8;
 static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max_depth, int rr_depth_arg, uint32_t flags) {
 	const bool count = flags & AGPT_FLAG_COUNTERS, timing = flags & AGPT_FLAG_TIMING, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
 	WaveQueues q[2];
@@ -427,41 +444,93 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	}
 	int* bucketOffsets = c->hist.p + 6 * AGPT_BUCKETS;
 	int* bucketRunning = c->hist.p + 7 * AGPT_BUCKETS;
-	const bool bucketActive = c->bucketActive;
-	const int* shadowQueue = q[0].shadow;
-	bool activeSorted = false;
-	const bool bucketing = c->bucketRays;
-	const int* closestQueue = q[0].closest;     // wave 0: camera rays in pixel order
-	int nClosest = n, nShadow = 0, nActive = n, cur = 0;
+	const bool bucketing = c->bucketRays, bucketActive = c->bucketActive;
 	float msClosest = 0, msAny = 0, msShade = 0;
 	unsigned long long* cntClosest = c->traceCounters.p;
 	unsigned long long* cntAny = c->traceCounters.p + 4;
-	while (nActive > 0) {
+
+	int ubClosest = n, ubShadow = 0, ubActive = n;   // upper bounds of the current wave's queue lengths
+	int cur = 0, wave = 0;
+	int ringHead = 0, ringTail = 0;                  // copies in flight: [ringTail, ringHead)
+	bool done = false;
+	while (!done) {
+		// ---- one wave on q[cur] -> q[cur ^ 1] ----
+		const int* closestQueue = q[cur].closest;
+		const int* shadowQueue = q[cur].shadow;
+		WaveQueues qin = q[cur];
+		if (wave > 0 && bucketing) {
+			// bucket pass: rays that start in the same cell going the same way end up adjacent
+			if (ubClosest > 0) {
+				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
+				k_bucket_scatter<<<Blocks(ubClosest, 256), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, q[cur].counts + 0, bucketOffsets, bucketRunning, c->sortedClosest.p);
+				c->stats.kernel_launches += 2;
+				closestQueue = c->sortedClosest.p;
+			}
+			if (ubShadow > 0) {
+				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].shadowHist, bucketOffsets, bucketRunning);
+				k_bucket_scatter<<<Blocks(ubShadow, 256), 256, 0, c->stream>>>(q[cur].shadow, q[cur].shadowKeys, q[cur].counts + 1, bucketOffsets, bucketRunning, c->sortedShadow.p);
+				c->stats.kernel_launches += 2;
+				shadowQueue = c->sortedShadow.p;
+			}
+			if (bucketActive && ubActive > 0) {
+				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].activeHist, bucketOffsets, bucketRunning);
+				k_bucket_scatter<<<Blocks(ubActive, 256), 256, 0, c->stream>>>(q[cur].active, q[cur].activeKeys, q[cur].counts + 2, bucketOffsets, bucketRunning, c->sortedActive.p);
+				c->stats.kernel_launches += 2;
+				qin.active = c->sortedActive.p;
+			}
+		}
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
-		if (nClosest > 0) {
-			LaunchClosest(count, strictBoxes, Blocks(nClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, nClosest, cntClosest);
+		if (ubClosest > 0) {
+			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest);
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
-		if (nShadow > 0) {
-			LaunchAny(count, strictBoxes, Blocks(nShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, nShadow, cntAny);
+		if (ubShadow > 0) {
+			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny);
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
-		CU(cudaMemsetAsync(q[cur ^ 1].hist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
-		CU(cudaMemsetAsync(q[cur ^ 1].shadowHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
-		CU(cudaMemsetAsync(q[cur ^ 1].activeHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+		if (bucketing) CU(cudaMemsetAsync(q[cur ^ 1].hist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+		if (bucketing) CU(cudaMemsetAsync(q[cur ^ 1].shadowHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+		if (bucketing && bucketActive) CU(cudaMemsetAsync(q[cur ^ 1].activeHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
-		sp.count = nActive; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
-		WaveQueues qin = q[cur];
-		if (activeSorted) qin.active = c->sortedActive.p;
-		k_shade<<<Blocks(nActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
+		if (c->envW > 0) k_shade<true><<<Blocks(ubActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		else k_shade<false><<<Blocks(ubActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
 		if (timing) CU(cudaEventRecord(c->evD, c->stream));
-		CU(cudaMemcpyAsync(c->hostCounts, q[cur ^ 1].counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-		CU(cudaStreamSynchronize(c->stream));
+		// counts of the NEXT wave -> pinned ring slot, marked by an event
+		int slot = ringHead % kRing;
+		CU(cudaMemcpyAsync(c->hostCounts + 3 * slot, q[cur ^ 1].counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaEventRecord(c->ringEvents[slot], c->stream));
+		ringHead++;
+		cur ^= 1; wave++;
+		c->stats.waves++;
+		// the next wave's bounds follow from this wave's: the active list only shrinks
+		ubClosest = 2 * ubActive < (int)(2 * c->capacity) ? 2 * ubActive : (int)(2 * c->capacity);
+		ubShadow = ubActive;
+
+		// ---- consume the copies that have landed (block only when too far ahead, or when timing) ----
+		while (ringTail < ringHead) {
+			int s = ringTail % kRing;
+			bool mustWait = timing || !c->asyncWaves || (ringHead - ringTail) >= kMaxAhead;
+			cudaError_t e = mustWait ? cudaEventSynchronize(c->ringEvents[s]) : cudaEventQuery(c->ringEvents[s]);
+			if (e == cudaErrorNotReady) break;
+			if (e != cudaSuccess) return Fail(AGPT_ERR_CUDA, std::string("wave loop: ") + cudaGetErrorString(e));
+			const int* hc = c->hostCounts + 3 * s;        // (closest, shadow, active) of wave ringTail + 1
+			int landedWave = ringTail + 1;
+			ringTail++;
+			if (hc[2] == 0) { done = true; break; }
+			if (landedWave == wave) { ubClosest = hc[0]; ubShadow = hc[1]; ubActive = hc[2]; }
+			else {
+				// older than the wave about to be launched: still bounds it
+				if (hc[2] < ubActive) ubActive = hc[2];
+				if (2 * hc[2] < ubClosest) ubClosest = 2 * hc[2];
+				if (hc[2] < ubShadow) ubShadow = hc[2];
+			}
+		}
 		if (timing) {
 			float a = 0, b = 0, d = 0;
 			cudaEventElapsedTime(&a, c->evA, c->evB);
@@ -469,31 +538,6 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 			cudaEventElapsedTime(&d, c->evC, c->evD);
 			msClosest += a; msAny += b; msShade += d;
 		}
-		nClosest = c->hostCounts[0]; nShadow = c->hostCounts[1]; nActive = c->hostCounts[2];
-		cur ^= 1;
-		closestQueue = q[cur].closest;
-		if (bucketing && nClosest > 0) {
-			// bucket pass: put rays that leave the same primitive in the same octant next to each other
-			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
-			k_bucket_scatter<<<Blocks(nClosest, 256), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, nClosest, bucketOffsets, bucketRunning, c->sortedClosest.p);
-			c->stats.kernel_launches += 2;
-			closestQueue = c->sortedClosest.p;
-		}
-		shadowQueue = q[cur].shadow;
-		if (bucketing && nShadow > 0) {
-			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].shadowHist, bucketOffsets, bucketRunning);
-			k_bucket_scatter<<<Blocks(nShadow, 256), 256, 0, c->stream>>>(q[cur].shadow, q[cur].shadowKeys, nShadow, bucketOffsets, bucketRunning, c->sortedShadow.p);
-			c->stats.kernel_launches += 2;
-			shadowQueue = c->sortedShadow.p;
-		}
-		activeSorted = false;
-		if (bucketing && bucketActive && nActive > 0) {
-			k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].activeHist, bucketOffsets, bucketRunning);
-			k_bucket_scatter<<<Blocks(nActive, 256), 256, 0, c->stream>>>(q[cur].active, q[cur].activeKeys, nActive, bucketOffsets, bucketRunning, c->sortedActive.p);
-			c->stats.kernel_launches += 2;
-			activeSorted = true;
-		}
-		c->stats.waves++;
 	}
 	c->stats.ms_trace_closest += msClosest; c->stats.ms_trace_any += msAny; c->stats.ms_shade += msShade;
 	return AGPT_OK;

@@ -119,18 +119,19 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const int* hist, int* offs
 }
 // ... and the scatter of the queue entries into bucket order (order inside a bucket is free:
 // every path's arithmetic is independent of its queue position).
-__global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned short* __restrict__ keys, int count,
+__global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned short* __restrict__ keys, const int* __restrict__ countPtr,
 		const int* __restrict__ offsets, int* running, int* __restrict__ out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool valid = i < count;
+	int entry = in[i], rawKey = keys[i];
+	bool valid = i < *countPtr;
 	int lane = threadIdx.x & 31;
-	int key = valid ? keys[i] : (AGPT_BUCKETS + lane);
+	int key = valid ? rawKey : (AGPT_BUCKETS + lane);
 	unsigned m = __match_any_sync(0xffffffffu, key);
 	int leader = __ffs(m) - 1;
 	int base = 0;
 	if (valid && lane == leader) base = atomicAdd(running + key, __popc(m));
 	base = __shfl_sync(0xffffffffu, base, leader);
-	if (valid) out[offsets[key] + base + __popc(m & ((1u << lane) - 1u))] = in[i];
+	if (valid) out[offsets[key] + base + __popc(m & ((1u << lane) - 1u))] = entry;
 }
 
 // ---- path generation: myapp.cpp:165-167 + Camera::GetRay (camera.h:58-64) ----------------
@@ -171,6 +172,7 @@ struct GenParams {
 
 __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQueues q, GenParams g) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0 && q.counts) { q.counts[0] = g.n; q.counts[1] = 0; q.counts[2] = g.n; }   // wave 0: n camera rays, n paths to shade
 	if (i >= g.n) return;
 	DRay ray;
 	uint32_t rng;
@@ -203,13 +205,18 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 
 // ---- trace kernels ---------------------------------------------------------------------
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	TraceCounters cnt = { 0, 0, 0, 0 };
+	// The queue length lives on the device (the host launches an upper bound of blocks).  The
+	// entry is fetched unconditionally -- queues are allocated with slack past any launchable
+	// index -- so that the two loads overlap instead of costing two dependent round trips.
+	int e = queue[i];
+	const int count = *countPtr;
 	bool lane = i < count;
-	int e = lane ? queue[i] : 0;
+	if (!lane) e = 0;
 	int path = e >> 1, kind = e & 1;
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) {
@@ -229,13 +236,15 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 }
 
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, int count,
+__global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
 		unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	TraceCounters cnt = { 0, 0, 0, 0 };
+	int path = queue[i];
+	const int count = *countPtr;
 	bool lane = i < count;
-	int path = lane ? queue[i] : 0;
+	if (!lane) path = 0;
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = ps.shO[path]; d = ps.shD[path]; }
 	HitRecord hit;
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 
 // ---- shade -------------------------------------------------------------------------------
 struct ShadeParams {
-	int count;            // entries in q.active (this wave)
+	const int* count;     // entries in q.active (this wave), on the device
 	int max_depth;
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
 };
@@ -284,10 +293,13 @@ __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
 #ifndef AGPT_SHADE_MIN_BLOCKS
 #define AGPT_SHADE_MIN_BLOCKS 1
 #endif
+// ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
+template <bool ENV>
 __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool valid = i < sp.count;
-	int path = valid ? qin.active[i] : 0;
+	int path = qin.active[i];          // unconditional (allocation slack), overlaps with the count load
+	bool valid = i < *sp.count;
+	if (!valid) path = 0;
 
 	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false;
 	int keyExtend = 0, keyMis = 0, keyShadow = 0;
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 				else {
 					for (int l = 0; l < sc.n_lights; l++) {
 						if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
-						else if (sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, D);
+						else if (ENV && sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, D);
 					}
 				}
 			}
@@ -409,7 +421,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 								}
 							}
 						}
-						else if (lightType == AGPT_LIGHT_INFINITE_AREA) {
+						else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) {
 							// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
 							// the visibility ray starts EPSILON along the GEOMETRIC normal
 							float u01 = RandomFloat(rng);
@@ -500,13 +512,13 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 							if (!IsBlack(f) && scatteringPdf > 0) {
 								float lp;
 								if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
-								else if (lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
+								else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
 								else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
 								if (lp != 0) {
 									float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
 									DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
 									// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
-									float3 LiMis = lightType == AGPT_LIGHT_INFINITE_AREA ? EnvLe(sc, mr.D) : lemit;
+									float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
 									float3 term = f * LiMis * weight / scatteringPdf;
 									ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
 									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);

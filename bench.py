@@ -142,7 +142,7 @@ def cpu_reference_run(defaults, level, target_seconds, threads):
     return dict(paths=paths, rays=rays, seconds=dt, cores=threads, sample=f"centred {cw}x{ch} crop of the {W}x{H} film, {spp} spp, all bounces")
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     pkg = load_pkg()
@@ -174,7 +174,7 @@ def run_reference(args, rank, world):
         out = {"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}
     if out is None:
         out = {"impl": "reference", "unavailable": "oracle/_ref/libagpt_ref.so not built (needs /root/reference at build time)"}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -192,12 +192,22 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: park fd 1 on stderr until then (NCCL / libraries may print)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -341,7 +351,7 @@ def main():
                        "api": "CudaPathTracer::Render over host Accumulator buffers", "steps": e2e_steps},
                "gpu_launches": int(launches),
                "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
