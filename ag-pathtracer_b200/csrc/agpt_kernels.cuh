@@ -87,7 +87,7 @@ __device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D) {
 	int cell = 0;
 #pragma unroll
 	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
-	return (cell << 3) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);
+	return (cell << 3) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
 }
 // Histogram add with one atomic per distinct key per warp.  All 32 lanes must call.
 __device__ __forceinline__ void WarpHistAdd(bool pred, int key, int* hist) {

@@ -15,15 +15,6 @@ struct agpt_host_tracer {
 	std::unique_ptr<CudaPathTracer> tracer;
 };
 
-inline float3 CudaPathTracer::Li(const Ray& ray, const Scene& scene, int depth) const {
-	if (uploaded != &scene) Upload(scene);
-	float r7[7] = { ray.O.x, ray.O.y, ray.O.z, ray.D.x, ray.D.y, ray.D.z, ray.t };
-	uint32_t seed = 0x12345678u + 0x9e3779b9u * liCalls++;   // upstream's global seed, advanced per call
-	float out[3] = { 0, 0, 0 };
-	Check(agpt_li_rays(ctx, 1, r7, &seed, MaxDepth, depth, out));
-	return float3(out[0], out[1], out[2]);
-}
-
 static thread_local std::string g_hostError;
 static int HostFail(const std::string& m) { g_hostError = m; return AGPT_ERR_INVALID; }
 #define HOST_TRY(...) try { __VA_ARGS__ } catch (const std::exception& e) { return HostFail(e.what()); }

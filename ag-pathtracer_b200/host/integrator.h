@@ -75,4 +75,14 @@ protected:
 	mutable unsigned liCalls = 0;
 };
 
+// (defined here so that the mirror stays header-only; libagpt.so is the only link dependency)
+inline float3 CudaPathTracer::Li(const Ray& ray, const Scene& scene, int depth) const {
+	if (uploaded != &scene) Upload(scene);
+	float r7[7] = { ray.O.x, ray.O.y, ray.O.z, ray.D.x, ray.D.y, ray.D.z, ray.t };
+	uint32_t seed = 0x12345678u + 0x9e3779b9u * liCalls++;   // upstream's global seed, advanced per call
+	float out[3] = { 0, 0, 0 };
+	Check(agpt_li_rays(ctx, 1, r7, &seed, MaxDepth, depth, out));
+	return float3(out[0], out[1], out[2]);
+}
+
 using PathTracer = CudaPathTracer;   // scene code written against the reference keeps compiling
