@@ -100,3 +100,49 @@ def test_error_paths(agpt):
     ctx.render(0, 0, 5)                          # empty sample range is a no-op
     assert not ctx.read_accum().any()
     ctx.close()
+
+
+@pytest.mark.parametrize("cfg,level", [(3, 4), (5, 4), (6, 2)])
+def test_filtered_slab_test_equals_strict(agpt, gpu_ctx, cfg, level):
+    """The exact-filtered slab test (reciprocal multiply + guard band) must take the same
+    decisions as the reference's six-division test: identical hits, identical visit / box /
+    triangle counts, identical radiance."""
+    d = agpt.config_defaults(cfg)
+    W, H = 192, 108
+    hs = agpt.HostScene(cfg, level)
+    hs.upload(gpu_ctx); gpu_ctx.set_film(W, H)
+    out = {}
+    for name, flag in (("filtered", 0), ("strict", agpt.FLAG_STRICT_BOXES)):
+        gpu_ctx.clear(); gpu_ctx.reset_stats()
+        hits = gpu_ctx.trace_primary(0, flag | agpt.FLAG_COUNTERS)
+        gpu_ctx.render(0, 4, d["max_depth"], d["depth_arg"], flag | agpt.FLAG_COUNTERS)
+        st = gpu_ctx.stats()
+        out[name] = (hits.copy(), gpu_ctx.read_accum(), (list(st.node_visits), list(st.box_tests), list(st.tri_tests), st.rays))
+    assert np.array_equal(out["filtered"][0].view(np.uint32), out["strict"][0].view(np.uint32))
+    assert np.array_equal(bits(out["filtered"][1]), bits(out["strict"][1]))
+    assert out["filtered"][2] == out["strict"][2]
+
+
+def test_bucketing_does_not_change_results(agpt):
+    """Queue order is free: with and without the ray-bucket pass the film is bit-identical."""
+    import os
+    cfg, level, W, H = 3, 3, 160, 90
+    d = agpt.config_defaults(cfg)
+    hs = agpt.HostScene(cfg, level)
+    films = []
+    for env in ({"AGPT_BUCKET_RAYS": "0"}, {"AGPT_BUCKET_RAYS": "1", "AGPT_BUCKET_ACTIVE": "1"}, {"AGPT_ASYNC_WAVES": "1"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            ctx = agpt.Context(0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        hs.upload(ctx); ctx.set_film(W, H)
+        ctx.render(0, 4, d["max_depth"], d["depth_arg"])
+        films.append(ctx.read_accum())
+        ctx.close()
+    assert np.array_equal(bits(films[0]), bits(films[1])) and np.array_equal(bits(films[0]), bits(films[2]))
