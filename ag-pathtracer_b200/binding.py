@@ -35,7 +35,7 @@ class Material(ctypes.Structure):  # agpt_material
 
 
 class Stats(ctypes.Structure):  # agpt_stats
-    _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip")] + \
+    _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "rays_mis_culled", "rays_tail_culled")] + \
                [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests")] + \
                [(n, c_uint64) for n in ("kernel_launches", "launches_closest", "launches_any", "launches_shade", "waves")] + \
                [(n, c_float) for n in ("ms_render", "ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other")]
@@ -49,7 +49,13 @@ class Stats(ctypes.Structure):  # agpt_stats
 
     @property
     def rays(self):
+        """Rays actually traced through the scene."""
         return self.rays_closest + self.rays_shadow + self.rays_mis
+
+    @property
+    def rays_reference_equivalent(self):
+        """Rays the reference's PathTracer::Li issues for the same paths (traced + provably useless ones not traced)."""
+        return self.rays + self.rays_mis_culled + self.rays_tail_culled
 
     def algorithmic_bytes(self, k):
         """64 B per interior visit + 48 B per triangle test + 32 B per analytic record

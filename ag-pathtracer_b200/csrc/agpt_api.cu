@@ -736,7 +736,7 @@ int agpt_get_stats(agpt_ctx* c, agpt_stats* out) {
 	for (int k = 0; k < 2; k++) {
 		out->node_visits[k] = tc[4 * k]; out->box_tests[k] = tc[4 * k + 1]; out->tri_tests[k] = tc[4 * k + 2]; out->analytic_tests[k] = tc[4 * k + 3];
 	}
-	out->rays_closest += rc.rays_closest; out->rays_shadow = rc.rays_shadow; out->rays_mis = rc.rays_mis; out->rays_skip = rc.rays_skip;
+	out->rays_closest += rc.rays_closest; out->rays_shadow = rc.rays_shadow; out->rays_mis = rc.rays_mis; out->rays_skip = rc.rays_skip; out->rays_mis_culled = rc.rays_mis_culled; out->rays_tail_culled = rc.rays_tail_culled;
 	out->ms_other = out->ms_render - out->ms_trace_closest - out->ms_trace_any - out->ms_shade;
 	return AGPT_OK;
 }

@@ -61,7 +61,7 @@ struct WaveQueues {
 };
 
 struct RayCounters {     // device-side totals, see agpt_stats
-	unsigned long long rays_closest, rays_shadow, rays_mis, rays_skip;
+	unsigned long long rays_closest, rays_shadow, rays_mis, rays_skip, rays_mis_culled, rays_tail_culled;
 };
 
 // ---- warp-aggregated append (warp-ballot ray-queue compaction) ---------------------------
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 	bool valid = i < *sp.count;
 	if (!valid) path = 0;
 
-	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false;
+	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false, misCulled = false, tailCulled = false;
 	int keyExtend = 0, keyMis = 0, keyShadow = 0;
 
 	if (valid) {
@@ -520,11 +520,22 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 									// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
 									float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
 									float3 term = f * LiMis * weight / scatteringPdf;
+									// An area light's MIS ray only ever contributes if its closest hit IS the light's
+									// shape (integrator.h:82-85).  If the ray misses that sphere outright -- the very
+									// Sphere::Intersect test Scene::Intersect would run, with the largest possible
+									// ray.t -- nothing it could hit matters, so it is not traced.  Same result, far
+									// fewer closest-hit rays for small or distant lights (Sphere::Pdf never checks
+									// that wi points at the sphere, intersectable.h:306-317, so upstream traces them all).
+									float tLight;
+									bool canReachLight = lightType != AGPT_LIGHT_AREA || SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
+									misCulled = !canReachLight;
 									ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
 									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
 									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
-									emitMis = true;
-									keyMis = RayBucket(sc, mr.O, mr.D);
+									if (canReachLight) {
+										emitMis = true;
+										keyMis = RayBucket(sc, mr.O, mr.D);
+									}
 								}
 							}
 						}
@@ -552,7 +563,7 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 						bounces++;
 						// the vertex at bounces == max_depth only adds emission, and only after a
 						// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
-						if (bounces >= sp.max_depth && !specularBounce) alive = false;
+						if (bounces >= sp.max_depth && !specularBounce) { alive = false; tailCulled = true; }
 					}
 					if (alive) {
 						DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
@@ -598,6 +609,8 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 	m = __ballot_sync(0xffffffffu, emitMis);    if (lane == 0 && m) atomicAdd(&rc->rays_mis, (unsigned long long)__popc(m));
 	m = __ballot_sync(0xffffffffu, emitShadow); if (lane == 0 && m) atomicAdd(&rc->rays_shadow, (unsigned long long)__popc(m));
 	m = __ballot_sync(0xffffffffu, skipRay);    if (lane == 0 && m) atomicAdd(&rc->rays_skip, (unsigned long long)__popc(m));
+	m = __ballot_sync(0xffffffffu, misCulled);  if (lane == 0 && m) atomicAdd(&rc->rays_mis_culled, (unsigned long long)__popc(m));
+	m = __ballot_sync(0xffffffffu, tailCulled); if (lane == 0 && m) atomicAdd(&rc->rays_tail_culled, (unsigned long long)__popc(m));
 }
 
 // ---- accumulate: myapp.cpp:169-173 + Accumulator::AddSample (myapp.h:17-19) --------------

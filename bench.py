@@ -269,12 +269,14 @@ def main():
     ms = ev0.elapsed_time(ev1)
     st = ctx.stats()
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    tot = torch.tensor([float(st.rays), float(st.paths), float(st.kernel_launches)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    tot = torch.tensor([float(st.rays), float(st.paths), float(st.kernel_launches), float(st.rays_reference_equivalent),
+                        float(st.rays_closest), float(st.rays_shadow), float(st.rays_mis), float(st.rays_mis_culled), float(st.rays_tail_culled)],
+                       dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
-    rays, paths, launches = [float(v) for v in tot.tolist()]
+    rays, paths, launches, rays_ref_eq, r_closest, r_shadow, r_mis, r_mis_culled, r_tail_culled = [float(v) for v in tot.tolist()]
     value = rays / ms_max / 1e3
 
     # ---- end-to-end through the reference-facing host API (host buffers in and out) -------
@@ -346,6 +348,13 @@ def main():
                           "scene_bytes": counts["bytes"], "parallelism": f"sample-index split x{world}, one NCCL all-reduce of the float4 accumulator",
                           "l2": "inputs larger than L2 (scene + wavefront state >> 126 MB); no flush needed"},
                "spp_per_s": paths / (W * H) / (ms_max * 1e-3), "Mpaths_per_s": paths / ms_max / 1e3,
+               # value counts rays actually traced through the scene.  The reference also traces rays whose
+               # outcome cannot matter (MIS rays that miss their light's sphere, the discarded ray at MaxDepth);
+               # the B200 path proves them useless and skips them, so spp/s is the like-for-like speed and
+               # ref_equivalent_Mrays_per_s is the throughput in the reference's own ray accounting.
+               "ref_equivalent_Mrays_per_s": rays_ref_eq / ms_max / 1e3,
+               "rays": {"closest_path": r_closest, "shadow": r_shadow, "mis_traced": r_mis, "mis_culled_exactly": r_mis_culled,
+                        "tail_culled_exactly": r_tail_culled},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": W * H * 16 + 76, "d2h_bytes_per_step": W * H * 16,
                        "api": "CudaPathTracer::Render over host Accumulator buffers", "steps": e2e_steps},
