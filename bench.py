@@ -282,7 +282,7 @@ def main():
     # ---- end-to-end through the reference-facing host API (host buffers in and out) -------
     tracer = pkg.HostTracer(depth, local_rank)
     host_acc, _film_owner = pkg.pinned_film(W, H)          # page-locked host film, as the host mirror's Accumulator allocates it
-    tracer.render(scene, W, H, host_acc, 0, 1, depth_arg)             # uploads the scene, warms up
+    tracer.render(scene, W, H, host_acc, 0, spp_step, depth_arg)      # uploads the scene, sizes the wavefront state, warms up
     e2e_steps = max(1, min(args.steps, 3))
     tctx_stats0 = None
     barrier()

@@ -48,3 +48,19 @@ def test_radiance_rmse(agpt, ref, gpu_ctx, config, level, W, H):
     # stronger than the gate: sin/cos/acos follow glibc's algorithms on the device, so whole
     # paths -- and with the same summation order the accumulators -- come out bit-identical
     assert exact >= 0.999
+
+
+@pytest.mark.parametrize("config,level,W,H", SMALL)
+def test_ray_accounting_matches_reference(agpt, gpu_ctx, config, level, W, H):
+    """Rays traced + rays proven useless and skipped == the rays the reference algorithm issues
+    (counted by the restatement, which is itself checked against the reference's own counts)."""
+    from oracle import port_binding as port
+    d = agpt.config_defaults(config)
+    hs = agpt.HostScene(config, level); ps = port.PortScene(hs)
+    hs.upload(gpu_ctx); gpu_ctx.set_film(W, H); gpu_ctx.clear(); gpu_ctx.reset_stats()
+    gpu_ctx.render(0, 2, d["max_depth"], d["depth_arg"])
+    st = gpu_ctx.stats()
+    _, cnt = ps.render(W, H, 0, 2, d["max_depth"], d["depth_arg"])
+    assert st.rays_shadow == cnt["rays_any"]
+    assert st.rays_closest + st.rays_mis + st.rays_mis_culled + st.rays_tail_culled == cnt["rays_closest"]
+    assert st.rays_reference_equivalent == cnt["rays_closest"] + cnt["rays_any"]
