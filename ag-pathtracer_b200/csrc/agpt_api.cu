@@ -496,8 +496,8 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
-		if (c->envW > 0) k_shade<true><<<Blocks(ubActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
-		else k_shade<false><<<Blocks(ubActive, 128), 128, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		if (c->envW > 0) k_shade<true><<<Blocks(ubActive, AGPT_SHADE_THREADS), AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		else k_shade<false><<<Blocks(ubActive, AGPT_SHADE_THREADS), AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
 		if (timing) CU(cudaEventRecord(c->evD, c->stream));

@@ -290,12 +290,29 @@ __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
 	return f3(0.f);
 }
 
-#ifndef AGPT_SHADE_MIN_BLOCKS
-#define AGPT_SHADE_MIN_BLOCKS 1
-#endif
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
+//
+// The kernel is ~100 KB of SASS (IEEE division / sqrt sequences, double-precision sincos), far
+// more than the instruction cache holds, and ncu shows "no instruction" as its top stall.  It is
+// written as top-level PHASES (A..E) and launched with one 512-thread block per SM, so that the
+// 16 resident warps start each block together and walk the same code regions at roughly the
+// same time.  Measured (cfg 3 / cfg 5 shade ms per 4 spp): 128-thread blocks 11.5 / 22.4,
+// 512-thread blocks 9.9 / 20.9; forcing lock-step with a block barrier after every phase
+// (AGPT_SHADE_PHASE_SYNC=1) costs more than it saves at 512 (10.7 / 23.0), so it is off.
+#ifndef AGPT_SHADE_THREADS
+#define AGPT_SHADE_THREADS 512
+#endif
+#ifndef AGPT_SHADE_PHASE_SYNC
+#define AGPT_SHADE_PHASE_SYNC 0
+#endif
+#if AGPT_SHADE_PHASE_SYNC
+#define SHADE_PHASE_BARRIER() __syncthreads()
+#else
+#define SHADE_PHASE_BARRIER() ((void)0)
+#endif
+
 template <bool ENV>
-__global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
+__global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	int path = qin.active[i];          // unconditional (allocation slack), overlaps with the count load
 	bool valid = i < *sp.count;
@@ -304,12 +321,22 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false, misCulled = false, tailCulled = false;
 	int keyExtend = 0, keyMis = 0, keyShadow = 0;
 
+	// state that lives across phases
+	uint32_t flags = 0;
+	float3 L = f3(0.f), beta = f3(0.f), D = f3(0.f);
+	bool finished = false, full = false, specularBounce = false;
+	int bounces = 0;
+	DSurface si;
+	si.p = f3(0.f); si.n = f3(0.f); si.sn = f3(0.f); si.sdpdu = f3(0.f);
+	const agpt_material* mat = sc.mats;
+
+	// ================= phase A: previous vertex's NEE, the new hit, its surface =================
 	if (valid) {
-		uint32_t flags = ps.flags[path];
+		flags = ps.flags[path];
 		float4 L4 = ps.L[path];
-		float3 L = f3(L4.x, L4.y, L4.z);
+		L = f3(L4.x, L4.y, L4.z);
 		float4 b4 = ps.beta[path];
-		float3 beta = f3(b4.x, b4.y, b4.z);
+		beta = f3(b4.x, b4.y, b4.z);
 		const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
 
 		// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
@@ -322,9 +349,9 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 			if (flags & PF_NEE_MIS) {
 				float4 t = ps.neeMis[path];
 				int lightIdx = __float_as_int(t.w);
-				int hitPrim = ps.misPrim[path];
+				int misHit = ps.misPrim[path];
 				bool lit;
-				if (hitPrim >= 0) lit = sc.prims[hitPrim].area_light == lightIdx;          // lightIsect.shape->GetAreaLight() == &light
+				if (misHit >= 0) lit = sc.prims[misHit].area_light == lightIdx;            // lightIsect.shape->GetAreaLight() == &light
 				else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
 				if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
 			}
@@ -333,17 +360,17 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 			flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
 		}
 
-		bool finished = false;
 		if (flags & PF_NO_CONTINUE) finished = true;
 		else {
 			// (2) the new vertex: ray and its closest hit
 			float4 o4 = ps.rayO[path], d4 = ps.rayD[path];
-			float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
+			float3 O = f3(o4.x, o4.y, o4.z);
+			D = f3(d4.x, d4.y, d4.z);
 			float4 h = ps.hitA[path];
 			int hitPrim = __float_as_int(h.w);
 			bool found = hitPrim >= 0;
-			int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
-			bool specularBounce = flags & PF_SPECULAR;
+			bounces = (int)(flags >> PF_BOUNCE_SHIFT);
+			specularBounce = flags & PF_SPECULAR;
 
 			// emitted light at the vertex or from the environment (integrator.h:139-147)
 			if (bounces == 0 || specularBounce) {
@@ -364,7 +391,6 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 			else {
 				agpt_prim prim = sc.prims[hitPrim];
 				// SurfaceInteraction of the closest hit
-				DSurface si;
 				if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
 				else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
 				else TriangleSurface(sc.meshes[prim.payload], ps.hitSlot[path], O, D, h.x, h.y, h.z, si);
@@ -377,211 +403,224 @@ __global__ void __launch_bounds__(128, AGPT_SHADE_MIN_BLOCKS) k_shade(DScene sc,
 					emitExtend = true; skipRay = true; stayActive = true;
 					keyExtend = RayBucket(sc, nr.O, nr.D);
 				}
-				else {
-					const agpt_material* mat = sc.mats + prim.material;
-					float3 wo = -D;
-					VertexBsdf vb;
-					VertexBsdfInit(vb, si, mat, wo);
-					uint32_t rng = ps.rng[path];
-					const bool doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
-
-					// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
-					// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
-					// (float2 arguments are evaluated right to left: .y first), then the two extra
-					// draws UniformInfiniteLight::Sample_Li makes (lights.cpp:15-24), then u (:171).
-					int numLight = 0;
-					float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0);
-					float3 wiL = f3(0.f), Li = f3(0.f), lemit = f3(0.f);
-					float lightPdf = 0;
-					DRay vis;
-					vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
-					int lightType = -1, lightPrimType = -1, lightPayload = 0;
-					if (doNee) {
-						int nLights = sc.n_lights;
-						numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
-						uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);
-						uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
-						const agpt_light& light = sc.lights[numLight];
-						lemit = f3(light.lemit);
-						lightType = light.type;
-						if (lightType == AGPT_LIGHT_AREA) {
-							// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
-							const agpt_prim& lp = sc.prims[light.prim];
-							lightPrimType = lp.type; lightPayload = lp.payload;
-							if (lp.type == AGPT_PRIM_SPHERE) {
-								float3 pS, nS;
-								SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
-								if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
-								else {
-									wiL = pS - si.p;
-									float dist = length(wiL);
-									wiL /= dist;
-									vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
-									Li = lemit;
-								}
-							}
-						}
-						else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) {
-							// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
-							// the visibility ray starts EPSILON along the GEOMETRIC normal
-							float u01 = RandomFloat(rng);
-							if (EnvSampleLi(sc, u01, &wiL, &lightPdf)) {
-								vis = MakeRay(si.p + AGPT_EPSILON * si.n, wiL);
-								Li = EnvLe(sc, vis.D);
-							}
-						}
-						else {
-							// UniformInfiniteLight::Sample_Li: RandomInHemisphere(shading.n), pdf 1/2pi
-							float a = 1 - 2 * RandomFloat(rng);
-							float b = sqrtf(1 - a * a);
-							float phi = 2 * AGPT_PI * RandomFloat(rng);
-							float sphi, cphi;
-							rsincos(phi, &sphi, &cphi);
-							float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
-							if (dot(v, si.sn) < 0) v = -v;
-							wiL = v;
-							lightPdf = AGPT_INV2PI;
-							vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL);
-							Li = lemit;
-						}
-					}
-					float2 u;
-					u.y = RandomFloat(rng); u.x = RandomFloat(rng);
-
-					// ---- directions: [0] light sample, [1] MIS sample, [2] continuation sample ----
-					const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
-					DirSample smp[2];
-#pragma unroll 1
-					for (int k = 0; k < 2; k++) {
-						bool want = k == 0 ? doNee : true;
-						if (want) SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, smp[k]);
-						else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
-					}
-					// ---- one evaluator, three directions ----
-					float3 fDir[3];
-					float pdfDir[3];
-					float3 wiWorld[3];
-#pragma unroll 1
-					for (int k = 0; k < 3; k++) {
-						fDir[k] = f3(0.f); pdfDir[k] = 0.f; wiWorld[k] = f3(0.f);
-						bool need = k == 0 ? (evalLight && vb.woOk) : (smp[k - 1].ok && smp[k - 1].lobe != AGPT_LOBE_SPECULAR);
-						float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : smp[k - 1].wi;
-						LobeEval ev;
-						ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
-						if (need) EvalLobes(vb, wiLoc, ev);
-						if (k == 0) {
-							if (need) {
-								// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
-								bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
-								fDir[0] = reflect ? ev.f : f3(0.f);
-								float p = 0.f;
-								if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
-								if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
-								if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
-								pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
-							}
-							wiWorld[0] = wiL;
-						}
-						else if (smp[k - 1].ok) {
-							wiWorld[k] = LocalToWorld(vb.b, smp[k - 1].wi);
-							fDir[k] = FinishSample(vb, smp[k - 1], ev, wiWorld[k], &pdfDir[k]);
-						}
-					}
-
-					// (3) EstimateDirect (integrator.h:38-93)
-					if (doNee) {
-						float scatteringPdf = 0;
-						if (evalLight) {
-							float3 f = fDir[0] * absdot(wiL, si.sn);
-							scatteringPdf = pdfDir[0];
-							if (!IsBlack(f)) {
-								float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
-								float3 term = f * Li * weight / lightPdf;
-								ps.neeLight[path] = make_float4(term.x, term.y, term.z, 0.f);
-								ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
-								ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
-								emitShadow = true;
-								keyShadow = RayBucket(sc, vis.O, vis.D);
-							}
-						}
-						if (smp[0].ok) {
-							float3 wim = wiWorld[1];
-							float3 f = fDir[1];
-							scatteringPdf = pdfDir[1];
-							f *= absdot(wim, si.sn);
-							if (!IsBlack(f) && scatteringPdf > 0) {
-								float lp;
-								if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
-								else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
-								else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
-								if (lp != 0) {
-									float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
-									DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
-									// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
-									float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
-									float3 term = f * LiMis * weight / scatteringPdf;
-									// An area light's MIS ray only ever contributes if its closest hit IS the light's
-									// shape (integrator.h:82-85).  If the ray misses that sphere outright -- the very
-									// Sphere::Intersect test Scene::Intersect would run, with the largest possible
-									// ray.t -- nothing it could hit matters, so it is not traced.  Same result, far
-									// fewer closest-hit rays for small or distant lights (Sphere::Pdf never checks
-									// that wi points at the sphere, intersectable.h:306-317, so upstream traces them all).
-									float tLight;
-									bool canReachLight = lightType != AGPT_LIGHT_AREA || SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
-									misCulled = !canReachLight;
-									ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
-									ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
-									ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
-									if (canReachLight) {
-										emitMis = true;
-										keyMis = RayBucket(sc, mr.O, mr.D);
-									}
-								}
-							}
-						}
-						if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
-					}
-
-					// (4) the new path direction (integrator.h:169-185)
-					float3 wi = wiWorld[2];
-					float pdf = pdfDir[2];
-					float3 f = fDir[2];
-					bool sampledSpecular = smp[1].lobe == AGPT_LOBE_SPECULAR;
-					bool alive = smp[1].ok && !(IsBlack(f) || pdf == 0);
-					if (alive) {
-						beta *= f * absdot(wi, si.sn) / pdf;
-						specularBounce = sampledSpecular;
-						// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
-						float maxComponent = smax(beta.x, smax(beta.y, beta.z));
-						if (maxComponent < 1 && sp.rr_depth_arg > 3) {
-							float q = smax(.05f, 1 - maxComponent);
-							if (RandomFloat(rng) < q) alive = false;
-							else beta /= 1 - q;
-						}
-					}
-					if (alive) {
-						bounces++;
-						// the vertex at bounces == max_depth only adds emission, and only after a
-						// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
-						if (bounces >= sp.max_depth && !specularBounce) { alive = false; tailCulled = true; }
-					}
-					if (alive) {
-						DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
-						ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
-						ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
-						ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
-						emitExtend = true; stayActive = true;
-						keyExtend = RayBucket(sc, nr.O, nr.D);
-					}
-					else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
-					else finished = true;
-					ps.rng[path] = rng;
-					flags = (flags & 0xffu & ~PF_SPECULAR) | (specularBounce ? PF_SPECULAR : 0u) | ((uint32_t)bounces << PF_BOUNCE_SHIFT);
-					if (emitShadow) flags |= PF_NEE_SHADOW;
-					if (emitMis) flags |= PF_NEE_MIS;
-				}
+				else { full = true; mat = sc.mats + prim.material; }
 			}
 		}
+	}
+	SHADE_PHASE_BARRIER();
+
+	// ================= phase B: BSDF frame, random numbers, light sample =================
+	const float3 wo = -D;
+	VertexBsdf vb;
+	uint32_t rng = 0;
+	bool doNee = false;
+	int numLight = 0;
+	float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0), u = make_float2(0, 0);
+	float3 wiL = f3(0.f), Li = f3(0.f), lemit = f3(0.f);
+	float lightPdf = 0;
+	DRay vis;
+	vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
+	int lightType = -1, lightPrimType = -1, lightPayload = 0;
+	VertexBsdfInit(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
+	if (full) {
+		rng = ps.rng[path];
+		doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
+		// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
+		// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
+		// (float2 arguments are evaluated right to left: .y first), then the extra draws the
+		// infinite lights' Sample_Li make (lights.cpp:15-24,50-55), then u (:171).
+		if (doNee) {
+			int nLights = sc.n_lights;
+			numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
+			uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);
+			uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
+			const agpt_light& light = sc.lights[numLight];
+			lemit = f3(light.lemit);
+			lightType = light.type;
+			if (lightType == AGPT_LIGHT_AREA) {
+				// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
+				const agpt_prim& lp = sc.prims[light.prim];
+				lightPrimType = lp.type; lightPayload = lp.payload;
+				if (lp.type == AGPT_PRIM_SPHERE) {
+					float3 pS, nS;
+					SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
+					if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
+					else {
+						wiL = pS - si.p;
+						float dist = length(wiL);
+						wiL /= dist;
+						vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
+						Li = lemit;
+					}
+				}
+			}
+			else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) {
+				// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
+				// the visibility ray starts EPSILON along the GEOMETRIC normal
+				float u01 = RandomFloat(rng);
+				if (EnvSampleLi(sc, u01, &wiL, &lightPdf)) {
+					vis = MakeRay(si.p + AGPT_EPSILON * si.n, wiL);
+					Li = EnvLe(sc, vis.D);
+				}
+			}
+			else {
+				// UniformInfiniteLight::Sample_Li: RandomInHemisphere(shading.n), pdf 1/2pi
+				float a = 1 - 2 * RandomFloat(rng);
+				float b = sqrtf(1 - a * a);
+				float phi = 2 * AGPT_PI * RandomFloat(rng);
+				float sphi, cphi;
+				rsincos(phi, &sphi, &cphi);
+				float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
+				if (dot(v, si.sn) < 0) v = -v;
+				wiL = v;
+				lightPdf = AGPT_INV2PI;
+				vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL);
+				Li = lemit;
+			}
+		}
+		u.y = RandomFloat(rng); u.x = RandomFloat(rng);
+	}
+	const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
+	SHADE_PHASE_BARRIER();
+
+	// ================= phase C: sample the MIS and the continuation directions =================
+	DirSample smp[2];
+#pragma unroll 1
+	for (int k = 0; k < 2; k++) {
+		bool want = full && (k == 0 ? doNee : true);
+		if (want) SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, smp[k]);
+		else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
+	}
+	SHADE_PHASE_BARRIER();
+
+	// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
+	float3 fDir[3];
+	float pdfDir[3];
+	float3 wiWorld[3];
+#pragma unroll 1
+	for (int k = 0; k < 3; k++) {
+		fDir[k] = f3(0.f); pdfDir[k] = 0.f; wiWorld[k] = f3(0.f);
+		bool sampled = k > 0 && smp[k - 1].ok;
+		bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && smp[k - 1].lobe != AGPT_LOBE_SPECULAR));
+		float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : smp[k > 0 ? k - 1 : 0].wi;
+		LobeEval ev;
+		ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
+		if (need) EvalLobes(vb, wiLoc, ev);
+		if (k == 0) {
+			if (need) {
+				// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
+				bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
+				fDir[0] = reflect ? ev.f : f3(0.f);
+				float p = 0.f;
+				if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
+				if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
+				if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
+				pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
+			}
+			wiWorld[0] = wiL;
+		}
+		else if (full && sampled) {
+			wiWorld[k] = LocalToWorld(vb.b, smp[k - 1].wi);
+			fDir[k] = FinishSample(vb, smp[k - 1], ev, wiWorld[k], &pdfDir[k]);
+		}
+		SHADE_PHASE_BARRIER();
+	}
+
+	// ================= phase E: EstimateDirect terms, throughput, next rays =================
+	if (full) {
+		// (3) EstimateDirect (integrator.h:38-93)
+		if (doNee) {
+			float scatteringPdf = 0;
+			if (evalLight) {
+				float3 f = fDir[0] * absdot(wiL, si.sn);
+				scatteringPdf = pdfDir[0];
+				if (!IsBlack(f)) {
+					float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
+					float3 term = f * Li * weight / lightPdf;
+					ps.neeLight[path] = make_float4(term.x, term.y, term.z, 0.f);
+					ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
+					ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
+					emitShadow = true;
+					keyShadow = RayBucket(sc, vis.O, vis.D);
+				}
+			}
+			if (smp[0].ok) {
+				float3 wim = wiWorld[1];
+				float3 f = fDir[1];
+				scatteringPdf = pdfDir[1];
+				f *= absdot(wim, si.sn);
+				if (!IsBlack(f) && scatteringPdf > 0) {
+					float lp;
+					if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
+					else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
+					else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
+					if (lp != 0) {
+						float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
+						DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
+						// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
+						float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
+						float3 term = f * LiMis * weight / scatteringPdf;
+						// An area light's MIS ray only ever contributes if its closest hit IS the light's
+						// shape (integrator.h:82-85).  If the ray misses that sphere outright -- the very
+						// Sphere::Intersect test Scene::Intersect would run, with the largest possible
+						// ray.t -- nothing it could hit matters, so it is not traced.  Same result, far
+						// fewer closest-hit rays for small or distant lights (Sphere::Pdf never checks
+						// that wi points at the sphere, intersectable.h:306-317, so upstream traces them all).
+						float tLight;
+						bool canReachLight = lightType != AGPT_LIGHT_AREA || SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
+						misCulled = !canReachLight;
+						ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
+						ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
+						ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
+						if (canReachLight) {
+							emitMis = true;
+							keyMis = RayBucket(sc, mr.O, mr.D);
+						}
+					}
+				}
+			}
+			if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+		}
+
+		// (4) the new path direction (integrator.h:169-185)
+		float3 wi = wiWorld[2];
+		float pdf = pdfDir[2];
+		float3 f = fDir[2];
+		bool sampledSpecular = smp[1].lobe == AGPT_LOBE_SPECULAR;
+		bool alive = smp[1].ok && !(IsBlack(f) || pdf == 0);
+		if (alive) {
+			beta *= f * absdot(wi, si.sn) / pdf;
+			specularBounce = sampledSpecular;
+			// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
+			float maxComponent = smax(beta.x, smax(beta.y, beta.z));
+			if (maxComponent < 1 && sp.rr_depth_arg > 3) {
+				float q = smax(.05f, 1 - maxComponent);
+				if (RandomFloat(rng) < q) alive = false;
+				else beta /= 1 - q;
+			}
+		}
+		if (alive) {
+			bounces++;
+			// the vertex at bounces == max_depth only adds emission, and only after a
+			// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
+			if (bounces >= sp.max_depth && !specularBounce) { alive = false; tailCulled = true; }
+		}
+		if (alive) {
+			DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
+			ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
+			ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
+			ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+			emitExtend = true; stayActive = true;
+			keyExtend = RayBucket(sc, nr.O, nr.D);
+		}
+		else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
+		else finished = true;
+		ps.rng[path] = rng;
+		flags = (flags & 0xffu & ~PF_SPECULAR) | (specularBounce ? PF_SPECULAR : 0u) | ((uint32_t)bounces << PF_BOUNCE_SHIFT);
+		if (emitShadow) flags |= PF_NEE_SHADOW;
+		if (emitMis) flags |= PF_NEE_MIS;
+	}
+	if (valid) {
 		ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
 		ps.flags[path] = flags;
 		if (finished) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);
