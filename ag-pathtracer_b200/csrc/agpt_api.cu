@@ -97,7 +97,13 @@ struct agpt_ctx {
 	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
 
-static const size_t kMaxPathsPerBatch = (size_t)1 << 23;   // 8.4 M path slots ~ 1.8 GB of wavefront state
+#ifndef AGPT_BATCH_LOG2
+#define AGPT_BATCH_LOG2 25
+#endif
+// Paths in flight per batch.  2^25 = 33.5 M slots ~ 8.5 GB of wavefront state + queues (sized for 180 GB of
+// HBM3e).  Bigger batches mean fuller waves and more rays per bucket, i.e. more coherent warps: cfg 3 at
+// 16 spp runs in 106 / 98 / 94 ms with 2^23 / 2^24 / 2^25 slots.
+static const size_t kMaxPathsPerBatch = (size_t)1 << AGPT_BATCH_LOG2;
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
