@@ -44,9 +44,13 @@ struct MeshStore {
 	void Free() { nodes.Free(); tris.Free(); normals.Free(); uvs.Free(); ids.Free(); }
 };
 
+static const int kWaveHistory = 64;
+
 struct agpt_ctx {
 	int device = 0;
 	cudaStream_t ownStream = nullptr, stream = nullptr;
+	cudaStream_t sideStream = nullptr;   // any-hit trace of a wave runs here, beside the closest-hit trace
+	cudaEvent_t evFork = nullptr, evJoin = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
 	int smCount = 0;
 
@@ -93,6 +97,10 @@ struct agpt_ctx {
 	bool asyncWaves = false;      // AGPT_ASYNC_WAVES=1: run one wave ahead of the landed queue counts instead of syncing
 	                              // every wave.  Measured slower (N=1: 133 vs 130.5 ms/step, N=8: 142.8 vs 139.3): the loose
 	                              // launch bounds and the extra empty wave cost more than the ~30 us sync gaps they remove.
+	bool overlapAny = true;       // AGPT_OVERLAP_ANY=0: any-hit trace on the main stream after the closest-hit trace
+	int shadeCompact = -1;        // AGPT_SHADE_COMPACT: 1 always, 0 never, -1 by the survival history below
+	float waveSurvival[kWaveHistory];   // share of wave w's shade entries that stayed active, last time seen (-1: never)
+	int shadeChunks = 8;          // AGPT_SHADE_CHUNKS: upper limit of 32-entry list pieces per shade warp
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
@@ -213,6 +221,8 @@ int agpt_create(int device, agpt_ctx** out) {
 	c->smCount = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	c->stream = c->ownStream;
+	CU(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
 	CU(c->hist.Alloc(8 * AGPT_BUCKETS));
@@ -223,6 +233,10 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaMallocHost((void**)&c->hostCounts, 8 * 3 * sizeof(int)));
 	for (auto& e : c->ringEvents) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
+	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
+	for (float& v : c->waveSurvival) v = -1.f;
+	if (const char* e = getenv("AGPT_SHADE_COMPACT")) c->shadeCompact = atoi(e);
+	if (const char* e = getenv("AGPT_SHADE_CHUNKS")) c->shadeChunks = atoi(e) > 0 ? atoi(e) : 1;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_ACTIVE")) c->bucketActive = atoi(e) != 0;
 	*out = c;
@@ -248,6 +262,8 @@ int agpt_destroy(agpt_ctx* c) {
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
 	for (auto& e : c->ringEvents) if (e) cudaEventDestroy(e);
 	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
+	cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin);
+	cudaStreamDestroy(c->sideStream);
 	cudaStreamDestroy(c->ownStream);
 	delete c;
 	return AGPT_OK;
@@ -266,6 +282,7 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	NEED(c != nullptr && n >= 0 && (n == 0 || meshes != nullptr), AGPT_ERR_INVALID, "bad mesh table");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	for (float& v : c->waveSurvival) v = -1.f;       // new scene: forget the per-wave survival history
 	for (auto& m : c->meshStore) m.Free();
 	c->meshStore.assign(n, MeshStore());
 	std::vector<DMesh> table(n);
@@ -348,6 +365,7 @@ int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
 	NEED(c != nullptr && cam != nullptr, AGPT_ERR_INVALID, "null camera");
 	c->cam = *cam;
 	c->haveCam = true;
+	for (float& v : c->waveSurvival) v = -1.f;
 	return AGPT_OK;
 }
 
@@ -451,11 +469,13 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	int* bucketOffsets = c->hist.p + 6 * AGPT_BUCKETS;
 	int* bucketRunning = c->hist.p + 7 * AGPT_BUCKETS;
 	const bool bucketing = c->bucketRays, bucketActive = c->bucketActive;
+	const bool overlap = c->overlapAny && !timing;
 	float msClosest = 0, msAny = 0, msShade = 0;
 	unsigned long long* cntClosest = c->traceCounters.p;
 	unsigned long long* cntAny = c->traceCounters.p + 4;
 
 	int ubClosest = n, ubShadow = 0, ubActive = n;   // upper bounds of the current wave's queue lengths
+	int shadedEntries[kRing] = {};                   // entries of the waves whose counts are still in flight
 	int cur = 0, wave = 0;
 	int ringHead = 0, ringTail = 0;                  // copies in flight: [ringTail, ringHead)
 	bool done = false;
@@ -485,13 +505,24 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 				qin.active = c->sortedActive.p;
 			}
 		}
+		// The two traces of a wave are independent (different queues, different result arrays):
+		// unless per-kernel timing is on, the any-hit trace runs on the side stream so that each
+		// fills the SMs the other's tail leaves idle.
+		const bool fork = overlap && ubClosest > 0 && ubShadow > 0;
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
+		if (fork) CU(cudaEventRecord(c->evFork, c->stream));
 		if (ubClosest > 0) {
 			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest);
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
-		if (ubShadow > 0) {
+		if (fork) {
+			CU(cudaStreamWaitEvent(c->sideStream, c->evFork, 0));
+			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->sideStream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny);
+			c->stats.kernel_launches++; c->stats.launches_any++;
+			CU(cudaEventRecord(c->evJoin, c->sideStream));
+			CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
+		} else if (ubShadow > 0) {
 			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny);
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
@@ -502,8 +533,26 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
-		if (c->envW > 0) k_shade<true><<<Blocks(ubActive, AGPT_SHADE_THREADS), AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
-		else k_shade<false><<<Blocks(ubActive, AGPT_SHADE_THREADS), AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		// Survivor compaction inside the shade blocks pays when a good part of the list is about to
+		// finish (open scenes: cfg 3 shade -22 %, cfg 4 -29 %); when most paths go on (closed rooms)
+		// its ring and barriers cost more than the denser warps save (cfg 5: +10 %).  How many
+		// entries of wave w stay active is almost the same from batch to batch of one scene, so the
+		// share seen the last time wave w was shaded decides; without history: compact.
+		const int wslot = wave < kWaveHistory ? wave : kWaveHistory - 1;
+		const bool compact = c->shadeCompact == 1 || (c->shadeCompact < 0 && (c->waveSurvival[wslot] < 0.f || c->waveSurvival[wslot] < 0.7f));
+		shadedEntries[wave % kRing] = ubActive;
+		int chunks = ubActive / (2 * c->smCount * AGPT_SHADE_THREADS);
+		chunks = chunks < 1 ? 1 : (chunks > c->shadeChunks ? c->shadeChunks : chunks);
+		sp.chunks = chunks;
+		const int shadeBlocks = Blocks(ubActive, AGPT_SHADE_THREADS * (compact ? chunks : 1));
+		if (c->envW > 0) {
+			if (compact) k_shade<true, true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+			else k_shade<true, false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		}
+		else {
+			if (compact) k_shade<false, true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+			else k_shade<false, false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+		}
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
 		if (timing) CU(cudaEventRecord(c->evD, c->stream));
@@ -529,6 +578,11 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 			int landedWave = ringTail + 1;
 			ringTail++;
 			if (hc[2] == 0) { done = true; break; }
+			{
+				// wave `landedWave - 1` kept hc[2] of its entries active
+				int w = landedWave - 1, ent = shadedEntries[w % kRing];
+				if (ent > 0) c->waveSurvival[w < kWaveHistory ? w : kWaveHistory - 1] = (float)hc[2] / (float)ent;
+			}
 			if (landedWave == wave) { ubClosest = hc[0]; ubShadow = hc[1]; ubActive = hc[2]; }
 			else {
 				// older than the wave about to be launched: still bounds it

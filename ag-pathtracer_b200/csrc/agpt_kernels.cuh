@@ -21,25 +21,46 @@
 #define PF_NO_CONTINUE   8u     // path ended at the previous vertex; only its NEE is left to fold in
 #define PF_BOUNCE_SHIFT  8
 
+// Path state streams through the chip once per kernel (>= 100 MB per wave, far more than any
+// reuse distance the caches could cover), while the BVH tables are re-read by every ray.  State
+// accesses therefore carry the cache-streaming hint (ld/st.global.cs = evict-first), so they do
+// not push nodes and triangles out of L2 between trace launches.
+#ifndef AGPT_STREAM_STATE
+#define AGPT_STREAM_STATE 0
+#endif
+template <typename T>
+struct StateRef {
+	T* p;
+	__device__ __forceinline__ operator T() const { return AGPT_STREAM_STATE ? __ldcs(p) : *p; }
+	__device__ __forceinline__ void operator=(const T& v) const { if (AGPT_STREAM_STATE) __stcs(p, v); else *p = v; }
+};
+template <typename T>
+struct StateArray {
+	T* p;
+	__host__ __device__ __forceinline__ StateArray& operator=(T* q) { p = q; return *this; }
+	__host__ __device__ __forceinline__ operator T*() const { return p; }
+	__device__ __forceinline__ StateRef<T> operator[](int i) const { return StateRef<T>{ p + i }; }
+};
+
 struct PathState {
-	float4* rayO;        // O.xyz, tmax
-	float4* rayD;        // D.xyz
-	float4* hitA;        // t, b1, b2, int_as_float(prim)
-	int* hitSlot;
-	float4* beta;        // throughput
-	float4* L;           // radiance so far
-	uint32_t* rng;
-	uint32_t* flags;
-	float4* neeLight;    // f*Li*weight/lightPdf of the light-sampling strategy (integrator.h:57)
-	float4* neeMis;      // f*Lemit*weight/scatteringPdf of the BSDF strategy (integrator.h:88); w = int_as_float(light index)
-	float4* neeBeta;     // beta at the vertex the estimate belongs to
-	float4* shO;         // shadow ray O.xyz, tmax
-	float4* shD;
-	float4* misO;        // MIS ray
-	float4* misD;
-	int* shadowOccluded;
-	int* misPrim;        // primitive hit by the MIS ray, -1 = none
-	float4* Lout;        // finished radiance per path slot
+	StateArray<float4> rayO;        // O.xyz, tmax
+	StateArray<float4> rayD;        // D.xyz
+	StateArray<float4> hitA;        // t, b1, b2, int_as_float(prim)
+	StateArray<int> hitSlot;
+	StateArray<float4> beta;        // throughput
+	StateArray<float4> L;           // radiance so far
+	StateArray<uint32_t> rng;
+	StateArray<uint32_t> flags;
+	StateArray<float4> neeLight;    // f*Li*weight/lightPdf of the light-sampling strategy (integrator.h:57)
+	StateArray<float4> neeMis;      // f*Lemit*weight/scatteringPdf of the BSDF strategy (integrator.h:88); w = int_as_float(light index)
+	StateArray<float4> neeBeta;     // beta at the vertex the estimate belongs to
+	StateArray<float4> shO;         // shadow ray O.xyz, tmax
+	StateArray<float4> shD;
+	StateArray<float4> misO;        // MIS ray
+	StateArray<float4> misD;
+	StateArray<int> shadowOccluded;
+	StateArray<int> misPrim;        // primitive hit by the MIS ray, -1 = none
+	StateArray<float4> Lout;        // finished radiance per path slot
 };
 
 #ifndef AGPT_CELL_BITS
@@ -282,6 +303,7 @@ struct ShadeParams {
 	const int* count;     // entries in q.active (this wave), on the device
 	int max_depth;
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
+	int chunks;           // 32-entry pieces of the active list per warp
 };
 
 __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
@@ -292,364 +314,420 @@ __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
 
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
 //
+// Shape of the kernel.  Most entries of the active list need almost no work: their path left
+// the scene, hit max depth or only waited for its last next-event estimate (cfg 3, second wave:
+// 2 of 3).  Shading them in place would leave the expensive part -- light sampling and three
+// BSDF evaluations -- running on a third of each warp.  So a block is a producer/consumer: it
+// reads one entry per thread (phase A: fold the previous vertex's NEE, emission, termination),
+// pushes the SURVIVORS into a ring in shared memory, and whenever a full block's worth of them
+// is waiting (or the block's share of the list is exhausted) runs one dense round of the
+// phases B..E on them.
+//
 // The kernel is ~100 KB of SASS (IEEE division / sqrt sequences, double-precision sincos), far
-// more than the instruction cache holds, and ncu shows "no instruction" as its top stall.  It is
-// written as top-level PHASES (A..E) and launched with one 512-thread block per SM, so that the
-// 16 resident warps start each block together and walk the same code regions at roughly the
-// same time.  Measured (cfg 3 / cfg 5 shade ms per 4 spp): 128-thread blocks 11.5 / 22.4,
-// 512-thread blocks 9.9 / 20.9; forcing lock-step with a block barrier after every phase
-// (AGPT_SHADE_PHASE_SYNC=1) costs more than it saves at 512 (10.7 / 23.0), so it is off.
+// more than the instruction cache holds, so it matters that the resident warps walk the same
+// code at roughly the same time: one large block per SM whose warps start every round together
+// (two barriers per round, both in the cheap part).  Measured: per-warp rings without barriers
+// reach the same 18 of 32 threads per instruction but stall on instruction fetch instead
+// (6.0 "no instruction" cycles per issue against 0.4) and gain nothing.
 #ifndef AGPT_SHADE_THREADS
-#define AGPT_SHADE_THREADS 512
+#define AGPT_SHADE_THREADS 768
 #endif
-#ifndef AGPT_SHADE_PHASE_SYNC
-#define AGPT_SHADE_PHASE_SYNC 0
-#endif
-#if AGPT_SHADE_PHASE_SYNC
-#define SHADE_PHASE_BARRIER() __syncthreads()
-#else
-#define SHADE_PHASE_BARRIER() ((void)0)
-#endif
+#define AGPT_SHADE_RING (2 * AGPT_SHADE_THREADS - 1)     // fewer than THREADS waiting + at most THREADS pushed
 
-template <bool ENV>
+template <bool ENV, bool COMPACT>
 __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	int path = qin.active[i];          // unconditional (allocation slack), overlaps with the count load
-	bool valid = i < *sp.count;
-	if (!valid) path = 0;
+	// survivors of phase A: {path, flags, L.x, L.y} and {L.z, beta.xyz}
+	__shared__ float4 ringA[COMPACT ? AGPT_SHADE_RING : 1];
+	__shared__ float4 ringB[COMPACT ? AGPT_SHADE_RING : 1];
+	__shared__ int ringTail;                                                // entries ever pushed
+	const int lane = threadIdx.x & 31;
+	const unsigned lanesBelow = (1u << lane) - 1u;
+	const int count = *sp.count;
+	const int chunks = COMPACT ? sp.chunks : 1;
+	int base = blockIdx.x * AGPT_SHADE_THREADS * chunks;                    // this block's share of the active list
+	const int end = min(base + AGPT_SHADE_THREADS * chunks, count);
+	int head = 0;                                                           // entries ever popped (block-uniform)
+	int nExtend = 0, nMis = 0, nShadow = 0, nSkip = 0, nMisCulled = 0, nTailCulled = 0;   // ray statistics (warp-uniform)
+	const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
+	if (COMPACT) {
+		if (threadIdx.x == 0) ringTail = 0;
+		__syncthreads();
+	}
 
-	bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false, misCulled = false, tailCulled = false;
-	int keyExtend = 0, keyMis = 0, keyShadow = 0;
+	while (true) {
+		// ================= phase A: previous vertex's NEE, emission, termination =================
+		bool survive = false;
+		int path = 0;
+		uint32_t flags = 0;
+		float3 L = f3(0.f), beta = f3(0.f);
+		float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, h = o4;
+		if (base < end) {
+			const int i = base + threadIdx.x;
+			if (i < end) {
+				path = qin.active[i];
+				flags = ps.flags[path];
+				h = ps.hitA[path];
+				if (!COMPACT || ENV) d4 = ps.rayD[path];
+				if (!COMPACT) o4 = ps.rayO[path];          // (a compacted survivor fetches its ray in its dense round)
+				float4 L4 = ps.L[path];
+				L = f3(L4.x, L4.y, L4.z);
+				float4 b4 = ps.beta[path];
+				beta = f3(b4.x, b4.y, b4.z);
 
-	// state that lives across phases
-	uint32_t flags = 0;
-	float3 L = f3(0.f), beta = f3(0.f), D = f3(0.f);
-	bool finished = false, full = false, specularBounce = false;
-	int bounces = 0;
-	DSurface si;
-	si.p = f3(0.f); si.n = f3(0.f); si.sn = f3(0.f); si.sdpdu = f3(0.f);
-	const agpt_material* mat = sc.mats;
-
-	// ================= phase A: previous vertex's NEE, the new hit, its surface =================
-	if (valid) {
-		flags = ps.flags[path];
-		float4 L4 = ps.L[path];
-		L = f3(L4.x, L4.y, L4.z);
-		float4 b4 = ps.beta[path];
-		beta = f3(b4.x, b4.y, b4.z);
-		const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
-
-		// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
-		if (flags & (PF_NEE_SHADOW | PF_NEE_MIS)) {
-			float3 Ld = f3(0.f);
-			if ((flags & PF_NEE_SHADOW) && !ps.shadowOccluded[path]) {
-				float4 t = ps.neeLight[path];
-				Ld += f3(t.x, t.y, t.z);
-			}
-			if (flags & PF_NEE_MIS) {
-				float4 t = ps.neeMis[path];
-				int lightIdx = __float_as_int(t.w);
-				int misHit = ps.misPrim[path];
-				bool lit;
-				if (misHit >= 0) lit = sc.prims[misHit].area_light == lightIdx;            // lightIsect.shape->GetAreaLight() == &light
-				else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
-				if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
-			}
-			float4 nb = ps.neeBeta[path];
-			L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
-			flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
-		}
-
-		if (flags & PF_NO_CONTINUE) finished = true;
-		else {
-			// (2) the new vertex: ray and its closest hit
-			float4 o4 = ps.rayO[path], d4 = ps.rayD[path];
-			float3 O = f3(o4.x, o4.y, o4.z);
-			D = f3(d4.x, d4.y, d4.z);
-			float4 h = ps.hitA[path];
-			int hitPrim = __float_as_int(h.w);
-			bool found = hitPrim >= 0;
-			bounces = (int)(flags >> PF_BOUNCE_SHIFT);
-			specularBounce = flags & PF_SPECULAR;
-
-			// emitted light at the vertex or from the environment (integrator.h:139-147)
-			if (bounces == 0 || specularBounce) {
-				if (found) {
-					int al = sc.prims[hitPrim].area_light;
-					if (al >= 0) L += beta * f3(sc.lights[al].lemit);
-					else L += beta * f3(0.f);
-				}
-				else {
-					for (int l = 0; l < sc.n_lights; l++) {
-						if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
-						else if (ENV && sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, D);
+				// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
+				if (flags & (PF_NEE_SHADOW | PF_NEE_MIS)) {
+					float3 Ld = f3(0.f);
+					if ((flags & PF_NEE_SHADOW) && !ps.shadowOccluded[path]) {
+						float4 t = ps.neeLight[path];
+						Ld += f3(t.x, t.y, t.z);
 					}
-				}
-			}
-
-			if (!found || bounces >= sp.max_depth) finished = true;     // integrator.h:150
-			else {
-				agpt_prim prim = sc.prims[hitPrim];
-				// SurfaceInteraction of the closest hit
-				if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
-				else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
-				else TriangleSurface(sc.meshes[prim.payload], ps.hitSlot[path], O, D, h.x, h.y, h.z, si);
-
-				if (prim.material < 0) {
-					// null material: pass straight through, bounce count unchanged (integrator.h:152-161)
-					DRay nr = MakeRay(si.p + AGPT_EPSILON * D, D);
-					ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
-					ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
-					emitExtend = true; skipRay = true; stayActive = true;
-					keyExtend = RayBucket(sc, nr.O, nr.D);
-				}
-				else { full = true; mat = sc.mats + prim.material; }
-			}
-		}
-	}
-	SHADE_PHASE_BARRIER();
-
-	// ================= phase B: BSDF frame, random numbers, light sample =================
-	const float3 wo = -D;
-	VertexBsdf vb;
-	uint32_t rng = 0;
-	bool doNee = false;
-	int numLight = 0;
-	float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0), u = make_float2(0, 0);
-	float3 wiL = f3(0.f), Li = f3(0.f), lemit = f3(0.f);
-	float lightPdf = 0;
-	DRay vis;
-	vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
-	int lightType = -1, lightPrimType = -1, lightPayload = 0;
-	VertexBsdfInit(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
-	if (full) {
-		rng = ps.rng[path];
-		doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
-		// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
-		// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
-		// (float2 arguments are evaluated right to left: .y first), then the extra draws the
-		// infinite lights' Sample_Li make (lights.cpp:15-24,50-55), then u (:171).
-		if (doNee) {
-			int nLights = sc.n_lights;
-			numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
-			uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);
-			uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
-			const agpt_light& light = sc.lights[numLight];
-			lemit = f3(light.lemit);
-			lightType = light.type;
-			if (lightType == AGPT_LIGHT_AREA) {
-				// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
-				const agpt_prim& lp = sc.prims[light.prim];
-				lightPrimType = lp.type; lightPayload = lp.payload;
-				if (lp.type == AGPT_PRIM_SPHERE) {
-					float3 pS, nS;
-					SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
-					if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
-					else {
-						wiL = pS - si.p;
-						float dist = length(wiL);
-						wiL /= dist;
-						vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
-						Li = lemit;
+					if (flags & PF_NEE_MIS) {
+						float4 t = ps.neeMis[path];
+						int lightIdx = __float_as_int(t.w);
+						int misHit = ps.misPrim[path];
+						bool lit;
+						if (misHit >= 0) lit = sc.prims[misHit].area_light == lightIdx;            // lightIsect.shape->GetAreaLight() == &light
+						else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
+						if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
 					}
+					float4 nb = ps.neeBeta[path];
+					L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
+					flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
 				}
-			}
-			else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) {
-				// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
-				// the visibility ray starts EPSILON along the GEOMETRIC normal
-				float u01 = RandomFloat(rng);
-				if (EnvSampleLi(sc, u01, &wiL, &lightPdf)) {
-					vis = MakeRay(si.p + AGPT_EPSILON * si.n, wiL);
-					Li = EnvLe(sc, vis.D);
+
+				if (!(flags & PF_NO_CONTINUE)) {
+					// (2) the new vertex: did the ray hit, and is there emission to add (integrator.h:139-147)
+					int hitPrim = __float_as_int(h.w);
+					bool found = hitPrim >= 0;
+					int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
+					if (bounces == 0 || (flags & PF_SPECULAR)) {
+						if (found) {
+							int al = sc.prims[hitPrim].area_light;
+							if (al >= 0) L += beta * f3(sc.lights[al].lemit);
+							else L += beta * f3(0.f);
+						}
+						else {
+							for (int l = 0; l < sc.n_lights; l++) {
+								if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
+								else if (ENV && sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, f3(d4.x, d4.y, d4.z));
+							}
+						}
+					}
+					survive = found && bounces < sp.max_depth;     // integrator.h:150
 				}
+				if (!survive) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);      // the path is complete
 			}
-			else {
-				// UniformInfiniteLight::Sample_Li: RandomInHemisphere(shading.n), pdf 1/2pi
-				float a = 1 - 2 * RandomFloat(rng);
-				float b = sqrtf(1 - a * a);
-				float phi = 2 * AGPT_PI * RandomFloat(rng);
-				float sphi, cphi;
-				rsincos(phi, &sphi, &cphi);
-				float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
-				if (dot(v, si.sn) < 0) v = -v;
-				wiL = v;
-				lightPdf = AGPT_INV2PI;
-				vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL);
-				Li = lemit;
-			}
+			base += AGPT_SHADE_THREADS;
 		}
-		u.y = RandomFloat(rng); u.x = RandomFloat(rng);
-	}
-	const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
-	SHADE_PHASE_BARRIER();
 
-	// ================= phase C: sample the MIS and the continuation directions =================
-	DirSample smp[2];
-#pragma unroll 1
-	for (int k = 0; k < 2; k++) {
-		bool want = full && (k == 0 ? doNee : true);
-		if (want) SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, smp[k]);
-		else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
-	}
-	SHADE_PHASE_BARRIER();
-
-	// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
-	float3 fDir[3];
-	float pdfDir[3];
-	float3 wiWorld[3];
-#pragma unroll 1
-	for (int k = 0; k < 3; k++) {
-		fDir[k] = f3(0.f); pdfDir[k] = 0.f; wiWorld[k] = f3(0.f);
-		bool sampled = k > 0 && smp[k - 1].ok;
-		bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && smp[k - 1].lobe != AGPT_LOBE_SPECULAR));
-		float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : smp[k > 0 ? k - 1 : 0].wi;
-		LobeEval ev;
-		ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
-		if (need) EvalLobes(vb, wiLoc, ev);
-		if (k == 0) {
-			if (need) {
-				// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
-				bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
-				fDir[0] = reflect ? ev.f : f3(0.f);
-				float p = 0.f;
-				if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
-				if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
-				if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
-				pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
+		bool valid = survive;
+		if (COMPACT) {
+			// push the survivors, then pop one dense round as soon as a block's worth is waiting
+			const unsigned m = __ballot_sync(0xffffffffu, survive);
+			int slot0 = 0;
+			if (lane == 0 && m) slot0 = atomicAdd(&ringTail, __popc(m));
+			slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+			if (survive) {
+				int s = (slot0 + __popc(m & lanesBelow)) % AGPT_SHADE_RING;
+				ringA[s] = make_float4(__int_as_float(path), __uint_as_float(flags), L.x, L.y);
+				ringB[s] = make_float4(L.z, beta.x, beta.y, beta.z);
 			}
-			wiWorld[0] = wiL;
-		}
-		else if (full && sampled) {
-			wiWorld[k] = LocalToWorld(vb.b, smp[k - 1].wi);
-			fDir[k] = FinishSample(vb, smp[k - 1], ev, wiWorld[k], &pdfDir[k]);
-		}
-		SHADE_PHASE_BARRIER();
-	}
-
-	// ================= phase E: EstimateDirect terms, throughput, next rays =================
-	if (full) {
-		// (3) EstimateDirect (integrator.h:38-93)
-		if (doNee) {
-			float scatteringPdf = 0;
-			if (evalLight) {
-				float3 f = fDir[0] * absdot(wiL, si.sn);
-				scatteringPdf = pdfDir[0];
-				if (!IsBlack(f)) {
-					float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
-					float3 term = f * Li * weight / lightPdf;
-					ps.neeLight[path] = make_float4(term.x, term.y, term.z, 0.f);
-					ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
-					ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
-					emitShadow = true;
-					keyShadow = RayBucket(sc, vis.O, vis.D);
-				}
+			__syncthreads();
+			const int pending = ringTail - head;
+			if (base < end && pending < AGPT_SHADE_THREADS) { __syncthreads(); continue; }     // keep collecting
+			if (pending == 0) break;
+			const int nRound = min(pending, AGPT_SHADE_THREADS);
+			valid = (int)threadIdx.x < nRound;
+			if (valid) {
+				int s = (head + (int)threadIdx.x) % AGPT_SHADE_RING;
+				float4 a = ringA[s], b = ringB[s];
+				path = __float_as_int(a.x); flags = __float_as_uint(a.y);
+				L = f3(a.z, a.w, b.x);
+				beta = f3(b.y, b.z, b.w);
 			}
-			if (smp[0].ok) {
-				float3 wim = wiWorld[1];
-				float3 f = fDir[1];
-				scatteringPdf = pdfDir[1];
-				f *= absdot(wim, si.sn);
-				if (!IsBlack(f) && scatteringPdf > 0) {
-					float lp;
-					if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
-					else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
-					else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
-					if (lp != 0) {
-						float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
-						DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
-						// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
-						float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
-						float3 term = f * LiMis * weight / scatteringPdf;
-						// An area light's MIS ray only ever contributes if its closest hit IS the light's
-						// shape (integrator.h:82-85).  If the ray misses that sphere outright -- the very
-						// Sphere::Intersect test Scene::Intersect would run, with the largest possible
-						// ray.t -- nothing it could hit matters, so it is not traced.  Same result, far
-						// fewer closest-hit rays for small or distant lights (Sphere::Pdf never checks
-						// that wi points at the sphere, intersectable.h:306-317, so upstream traces them all).
-						float tLight;
-						bool canReachLight = lightType != AGPT_LIGHT_AREA || SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
-						misCulled = !canReachLight;
-						ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
-						ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
-						ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
-						if (canReachLight) {
-							emitMis = true;
-							keyMis = RayBucket(sc, mr.O, mr.D);
+			head += nRound;
+			__syncthreads();                   // records are in registers: the next phase A may push again
+			if (!__any_sync(0xffffffffu, valid)) continue;
+			if (valid) { o4 = ps.rayO[path]; d4 = ps.rayD[path]; h = ps.hitA[path]; }
+		}
+
+		// ================= one dense round: phases B..E for the survivors =================
+		const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
+		bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false, misCulled = false, tailCulled = false;
+		int keyExtend = 0, keyMis = 0, keyShadow = 0;
+		bool finished = false, full = false;
+		bool specularBounce = flags & PF_SPECULAR;
+		int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
+		DSurface si;
+		si.p = f3(0.f); si.n = f3(0.f); si.sn = f3(0.f); si.sdpdu = f3(0.f);
+		const agpt_material* mat = sc.mats;
+
+		// the surface at the hit (a survivor has one); null materials pass straight through
+		if (valid) {
+			agpt_prim prim = sc.prims[__float_as_int(h.w)];
+			// SurfaceInteraction of the closest hit
+			if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
+			else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
+			else TriangleSurface(sc.meshes[prim.payload], ps.hitSlot[path], O, D, h.x, h.y, h.z, si);
+
+			if (prim.material < 0) {
+				// null material: pass straight through, bounce count unchanged (integrator.h:152-161)
+				DRay nr = MakeRay(si.p + AGPT_EPSILON * D, D);
+				ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
+				ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
+				emitExtend = true; skipRay = true; stayActive = true;
+				keyExtend = RayBucket(sc, nr.O, nr.D);
+			}
+			else { full = true; mat = sc.mats + prim.material; }
+		}
+
+		// ================= phase B: BSDF frame, random numbers, light sample =================
+		const float3 wo = -D;
+		VertexBsdf vb;
+		uint32_t rng = 0;
+		bool doNee = false;
+		int numLight = 0;
+		float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0), u = make_float2(0, 0);
+		float3 wiL = f3(0.f), Li = f3(0.f), lemit = f3(0.f);
+		float lightPdf = 0;
+		DRay vis;
+		vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
+		int lightType = -1, lightPrimType = -1, lightPayload = 0;
+		VertexBsdfInit(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
+		if (full) {
+			rng = ps.rng[path];
+			doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
+			// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
+			// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
+			// (float2 arguments are evaluated right to left: .y first), then the extra draws the
+			// infinite lights' Sample_Li make (lights.cpp:15-24,50-55), then u (:171).
+			if (doNee) {
+				int nLights = sc.n_lights;
+				numLight = min((int)(RandomFloat(rng) * nLights), nLights - 1);
+				uLight.y = RandomFloat(rng); uLight.x = RandomFloat(rng);
+				uScattering.y = RandomFloat(rng); uScattering.x = RandomFloat(rng);
+				const agpt_light& light = sc.lights[numLight];
+				lemit = f3(light.lemit);
+				lightType = light.type;
+				if (lightType == AGPT_LIGHT_AREA) {
+					// AreaLight::Sample_Li (lights.cpp:115-126); only spheres can be sampled
+					const agpt_prim& lp = sc.prims[light.prim];
+					lightPrimType = lp.type; lightPayload = lp.payload;
+					if (lp.type == AGPT_PRIM_SPHERE) {
+						float3 pS, nS;
+						SphereSampleFrom(sc.spheres[lp.payload], si.p, uLight, &pS, &nS, &lightPdf);
+						if (lightPdf == 0 || sqrLength(pS - si.p) == 0) lightPdf = 0;
+						else {
+							wiL = pS - si.p;
+							float dist = length(wiL);
+							wiL /= dist;
+							vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL, dist - 10 * AGPT_EPSILON);
+							Li = lemit;
 						}
 					}
 				}
+				else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) {
+					// InfiniteAreaLight::Sample_Li (lights.cpp:50-90): ignores u, one extra draw;
+					// the visibility ray starts EPSILON along the GEOMETRIC normal
+					float u01 = RandomFloat(rng);
+					if (EnvSampleLi(sc, u01, &wiL, &lightPdf)) {
+						vis = MakeRay(si.p + AGPT_EPSILON * si.n, wiL);
+						Li = EnvLe(sc, vis.D);
+					}
+				}
+				else {
+					// UniformInfiniteLight::Sample_Li: RandomInHemisphere(shading.n), pdf 1/2pi
+					float a = 1 - 2 * RandomFloat(rng);
+					float b = sqrtf(1 - a * a);
+					float phi = 2 * AGPT_PI * RandomFloat(rng);
+					float sphi, cphi;
+					rsincos(phi, &sphi, &cphi);
+					float3 v = f3(1.f * b * cphi, 1.f * b * sphi, 1.f * a);
+					if (dot(v, si.sn) < 0) v = -v;
+					wiL = v;
+					lightPdf = AGPT_INV2PI;
+					vis = MakeRay(si.p + AGPT_EPSILON * wiL, wiL);
+					Li = lemit;
+				}
 			}
-			if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+			u.y = RandomFloat(rng); u.x = RandomFloat(rng);
+		}
+		const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
+
+		// ================= phase C: sample the MIS and the continuation directions =================
+		DirSample smp[2];
+	#pragma unroll 1
+		for (int k = 0; k < 2; k++) {
+			bool want = full && (k == 0 ? doNee : true);
+			if (want) SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, smp[k]);
+			else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
 		}
 
-		// (4) the new path direction (integrator.h:169-185)
-		float3 wi = wiWorld[2];
-		float pdf = pdfDir[2];
-		float3 f = fDir[2];
-		bool sampledSpecular = smp[1].lobe == AGPT_LOBE_SPECULAR;
-		bool alive = smp[1].ok && !(IsBlack(f) || pdf == 0);
-		if (alive) {
-			beta *= f * absdot(wi, si.sn) / pdf;
-			specularBounce = sampledSpecular;
-			// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
-			float maxComponent = smax(beta.x, smax(beta.y, beta.z));
-			if (maxComponent < 1 && sp.rr_depth_arg > 3) {
-				float q = smax(.05f, 1 - maxComponent);
-				if (RandomFloat(rng) < q) alive = false;
-				else beta /= 1 - q;
+		// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
+		float3 fDir[3];
+		float pdfDir[3];
+		float3 wiWorld[3];
+	#pragma unroll 1
+		for (int k = 0; k < 3; k++) {
+			fDir[k] = f3(0.f); pdfDir[k] = 0.f; wiWorld[k] = f3(0.f);
+			bool sampled = k > 0 && smp[k - 1].ok;
+			bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && smp[k - 1].lobe != AGPT_LOBE_SPECULAR));
+			float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : smp[k > 0 ? k - 1 : 0].wi;
+			LobeEval ev;
+			ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
+			if (need) EvalLobes(vb, wiLoc, ev);
+			if (k == 0) {
+				if (need) {
+					// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
+					bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
+					fDir[0] = reflect ? ev.f : f3(0.f);
+					float p = 0.f;
+					if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
+					if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
+					if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
+					pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
+				}
+				wiWorld[0] = wiL;
 			}
+			else if (full && sampled) {
+				wiWorld[k] = LocalToWorld(vb.b, smp[k - 1].wi);
+				fDir[k] = FinishSample(vb, smp[k - 1], ev, wiWorld[k], &pdfDir[k]);
+			}
+			}
+
+		// ================= phase E: EstimateDirect terms, throughput, next rays =================
+		if (full) {
+			// (3) EstimateDirect (integrator.h:38-93)
+			if (doNee) {
+				float scatteringPdf = 0;
+				if (evalLight) {
+					float3 f = fDir[0] * absdot(wiL, si.sn);
+					scatteringPdf = pdfDir[0];
+					if (!IsBlack(f)) {
+						float weight = PowerHeuristic(1, lightPdf, 1, scatteringPdf);
+						float3 term = f * Li * weight / lightPdf;
+						ps.neeLight[path] = make_float4(term.x, term.y, term.z, 0.f);
+						ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
+						ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
+						emitShadow = true;
+						keyShadow = RayBucket(sc, vis.O, vis.D);
+					}
+				}
+				if (smp[0].ok) {
+					float3 wim = wiWorld[1];
+					float3 f = fDir[1];
+					scatteringPdf = pdfDir[1];
+					f *= absdot(wim, si.sn);
+					if (!IsBlack(f) && scatteringPdf > 0) {
+						float lp;
+						if (lightType == AGPT_LIGHT_AREA) lp = lightPrimType == AGPT_PRIM_SPHERE ? SpherePdfFrom(sc.spheres[lightPayload], si.p) : 0.f;
+						else if (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) lp = EnvPdfLi(sc, wim);
+						else lp = dot(si.n, wim) > 0 ? AGPT_INV2PI : 0.f;       // lights.cpp:26-28 (geometric n)
+						if (lp != 0) {
+							float weight = PowerHeuristic(1, scatteringPdf, 1, lp);
+							DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
+							// radiance the MIS ray returns if it reaches this light (integrator.h:81-87)
+							float3 LiMis = (ENV && lightType == AGPT_LIGHT_INFINITE_AREA) ? EnvLe(sc, mr.D) : lemit;
+							float3 term = f * LiMis * weight / scatteringPdf;
+							// An area light's MIS ray only ever contributes if its closest hit IS the light's
+							// shape (integrator.h:82-85).  If the ray misses that sphere outright -- the very
+							// Sphere::Intersect test Scene::Intersect would run, with the largest possible
+							// ray.t -- nothing it could hit matters, so it is not traced.  Same result, far
+							// fewer closest-hit rays for small or distant lights (Sphere::Pdf never checks
+							// that wi points at the sphere, intersectable.h:306-317, so upstream traces them all).
+							float tLight;
+							bool canReachLight = lightType != AGPT_LIGHT_AREA || SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
+							misCulled = !canReachLight;
+							ps.neeMis[path] = make_float4(term.x, term.y, term.z, __int_as_float(numLight));
+							ps.misO[path] = make_float4(mr.O.x, mr.O.y, mr.O.z, mr.t);
+							ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
+							if (canReachLight) {
+								emitMis = true;
+								keyMis = RayBucket(sc, mr.O, mr.D);
+							}
+						}
+					}
+				}
+				if (emitShadow || emitMis) ps.neeBeta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+			}
+
+			// (4) the new path direction (integrator.h:169-185)
+			float3 wi = wiWorld[2];
+			float pdf = pdfDir[2];
+			float3 f = fDir[2];
+			bool sampledSpecular = smp[1].lobe == AGPT_LOBE_SPECULAR;
+			bool alive = smp[1].ok && !(IsBlack(f) || pdf == 0);
+			if (alive) {
+				beta *= f * absdot(wi, si.sn) / pdf;
+				specularBounce = sampledSpecular;
+				// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
+				float maxComponent = smax(beta.x, smax(beta.y, beta.z));
+				if (maxComponent < 1 && sp.rr_depth_arg > 3) {
+					float q = smax(.05f, 1 - maxComponent);
+					if (RandomFloat(rng) < q) alive = false;
+					else beta /= 1 - q;
+				}
+			}
+			if (alive) {
+				bounces++;
+				// the vertex at bounces == max_depth only adds emission, and only after a
+				// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
+				if (bounces >= sp.max_depth && !specularBounce) { alive = false; tailCulled = true; }
+			}
+			if (alive) {
+				DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
+				ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
+				ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
+				ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
+				emitExtend = true; stayActive = true;
+				keyExtend = RayBucket(sc, nr.O, nr.D);
+			}
+			else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
+			else finished = true;
+			ps.rng[path] = rng;
+			flags = (flags & 0xffu & ~PF_SPECULAR) | (specularBounce ? PF_SPECULAR : 0u) | ((uint32_t)bounces << PF_BOUNCE_SHIFT);
+			if (emitShadow) flags |= PF_NEE_SHADOW;
+			if (emitMis) flags |= PF_NEE_MIS;
 		}
-		if (alive) {
-			bounces++;
-			// the vertex at bounces == max_depth only adds emission, and only after a
-			// specular bounce (integrator.h:139,150): otherwise its ray need not be traced
-			if (bounces >= sp.max_depth && !specularBounce) { alive = false; tailCulled = true; }
+		if (valid) {
+			ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
+			ps.flags[path] = flags;
+			if (finished) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);
 		}
-		if (alive) {
-			DRay nr = MakeRay(si.p + AGPT_EPSILON * wi, wi);
-			ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
-			ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
-			ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
-			emitExtend = true; stayActive = true;
-			keyExtend = RayBucket(sc, nr.O, nr.D);
-		}
-		else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
-		else finished = true;
-		ps.rng[path] = rng;
-		flags = (flags & 0xffu & ~PF_SPECULAR) | (specularBounce ? PF_SPECULAR : 0u) | ((uint32_t)bounces << PF_BOUNCE_SHIFT);
-		if (emitShadow) flags |= PF_NEE_SHADOW;
-		if (emitMis) flags |= PF_NEE_MIS;
-	}
-	if (valid) {
-		ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
-		ps.flags[path] = flags;
-		if (finished) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);
+
+		// (5) queue the next wave: one atomic per warp per queue
+		int slot = WarpAppend(emitExtend, qout.counts + 0);
+		if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
+		WarpHistAdd(emitExtend, keyExtend, qout.hist);
+		slot = WarpAppend(emitMis, qout.counts + 0);
+		if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
+		WarpHistAdd(emitMis, keyMis, qout.hist);
+		slot = WarpAppend(emitShadow, qout.counts + 1);
+		if (emitShadow) { qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
+		WarpHistAdd(emitShadow, keyShadow, qout.shadowHist);
+		slot = WarpAppend(stayActive, qout.counts + 2);
+		int keyActive = emitExtend ? keyExtend : 0;      // paths that only wait for their NEE go to bucket 0
+		if (stayActive) { qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
+		WarpHistAdd(stayActive, keyActive, qout.activeHist);
+
+		nExtend += __popc(__ballot_sync(0xffffffffu, emitExtend));
+		nMis += __popc(__ballot_sync(0xffffffffu, emitMis));
+		nShadow += __popc(__ballot_sync(0xffffffffu, emitShadow));
+		nSkip += __popc(__ballot_sync(0xffffffffu, skipRay));
+		nMisCulled += __popc(__ballot_sync(0xffffffffu, misCulled));
+		nTailCulled += __popc(__ballot_sync(0xffffffffu, tailCulled));
+		if (!COMPACT) break;
 	}
 
-	// (5) queue the next wave: one atomic per warp per queue
-	int slot = WarpAppend(emitExtend, qout.counts + 0);
-	if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
-	WarpHistAdd(emitExtend, keyExtend, qout.hist);
-	slot = WarpAppend(emitMis, qout.counts + 0);
-	if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
-	WarpHistAdd(emitMis, keyMis, qout.hist);
-	slot = WarpAppend(emitShadow, qout.counts + 1);
-	if (emitShadow) { qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
-	WarpHistAdd(emitShadow, keyShadow, qout.shadowHist);
-	slot = WarpAppend(stayActive, qout.counts + 2);
-	int keyActive = emitExtend ? keyExtend : 0;      // paths that only wait for their NEE go to bucket 0
-	if (stayActive) { qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
-	WarpHistAdd(stayActive, keyActive, qout.activeHist);
-
-	// ray statistics (warp-reduced)
-	unsigned m;
-	int lane = threadIdx.x & 31;
-	m = __ballot_sync(0xffffffffu, emitExtend); if (lane == 0 && m) atomicAdd(&rc->rays_closest, (unsigned long long)__popc(m));
-	m = __ballot_sync(0xffffffffu, emitMis);    if (lane == 0 && m) atomicAdd(&rc->rays_mis, (unsigned long long)__popc(m));
-	m = __ballot_sync(0xffffffffu, emitShadow); if (lane == 0 && m) atomicAdd(&rc->rays_shadow, (unsigned long long)__popc(m));
-	m = __ballot_sync(0xffffffffu, skipRay);    if (lane == 0 && m) atomicAdd(&rc->rays_skip, (unsigned long long)__popc(m));
-	m = __ballot_sync(0xffffffffu, misCulled);  if (lane == 0 && m) atomicAdd(&rc->rays_mis_culled, (unsigned long long)__popc(m));
-	m = __ballot_sync(0xffffffffu, tailCulled); if (lane == 0 && m) atomicAdd(&rc->rays_tail_culled, (unsigned long long)__popc(m));
+	// ray statistics: one atomic per counter per warp
+	if (lane == 0) {
+		if (nExtend) atomicAdd(&rc->rays_closest, (unsigned long long)nExtend);
+		if (nMis) atomicAdd(&rc->rays_mis, (unsigned long long)nMis);
+		if (nShadow) atomicAdd(&rc->rays_shadow, (unsigned long long)nShadow);
+		if (nSkip) atomicAdd(&rc->rays_skip, (unsigned long long)nSkip);
+		if (nMisCulled) atomicAdd(&rc->rays_mis_culled, (unsigned long long)nMisCulled);
+		if (nTailCulled) atomicAdd(&rc->rays_tail_culled, (unsigned long long)nTailCulled);
+	}
 }
 
 // ---- accumulate: myapp.cpp:169-173 + Accumulator::AddSample (myapp.h:17-19) --------------

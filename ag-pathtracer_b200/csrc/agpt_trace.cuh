@@ -54,8 +54,24 @@ struct NodeBox {
 	float3 bmin, bmax;
 	int first, count;
 };
+// BVH table loads.  AGPT_L2_KEEP=1 tags them L2::evict_last (createpolicy + cache_hint) so the
+// trees outlive the path-state streams in L2.
+#ifndef AGPT_L2_KEEP
+#define AGPT_L2_KEEP 0
+#endif
+__device__ __forceinline__ float4 LoadTable(const float4* __restrict__ p) {
+#if AGPT_L2_KEEP
+	unsigned long long pol;
+	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	float4 v;
+	asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+	return v;
+#else
+	return __ldg(p);
+#endif
+}
 __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, int i) {
-	float4 a = __ldg(nodes + 2 * i), b = __ldg(nodes + 2 * i + 1);
+	float4 a = LoadTable(nodes + 2 * i), b = LoadTable(nodes + 2 * i + 1);
 	NodeBox n;
 	n.bmin = f3(a.x, a.y, a.z);
 	n.bmax = f3(a.w, b.x, b.y);
@@ -64,8 +80,26 @@ __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, in
 	return n;
 }
 
-// A RUN of consecutive mesh primitives [p0, p1) of Scene::primitives.  `stack` points at this
-// thread's shared-memory column (stride = blockDim.x).  ANY: stop at the first accepted
+// Exact hit/miss decision of Bounds::Intersect (bvhtrimesh.h:18-36): filtered arithmetic first,
+// the reference's divisions only when a comparison falls inside the guard band.
+template <bool FAST>
+__device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, float3 D, float3 rD, bool filterOk, float rayT) {
+	if (FAST && filterOk) {
+		float tn, tx;
+		SlabApprox(bmin, bmax, O, rD, rayT, tn, tx);
+		int c = SlabDecision(tn, tx);
+		if (c >= 0) return c == 1;
+	}
+	float dist;
+	return BoundsIntersect(bmin, bmax, O, D, rayT, dist);
+}
+
+#ifndef AGPT_PREFETCH_TRI
+#define AGPT_PREFETCH_TRI 0      // prefetch the triangle of a single-triangle leaf as soon as the walk decides to visit it next
+#endif
+
+// A RUN of at most 32 consecutive mesh primitives [p0, p1) of Scene::primitives.  `stack` points
+// at this thread's shared-memory column (stride = blockDim.x).  ANY: stop at the first accepted
 // triangle.  Otherwise updates hit / rayT.
 //
 // Convergence: the walk is a WARP-SYNCHRONOUS loop.  All 32 lanes stay in the loop until
@@ -75,10 +109,13 @@ __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, in
 // `continue`d early run ahead as separate fragments (measured: 2.3-3.1 of 32 threads active
 // per instruction with the naive while/continue form, 7-23 with this one).
 //
-// Each lane walks the meshes of the run in list order on its own: a lane whose ray misses a
-// mesh's root box (bvhtrimesh.h:187) moves on to the next mesh at once instead of idling
-// until the slowest lane of the warp has finished that mesh.  Per ray the sequence of box
-// and triangle tests is exactly the reference's; only the interleaving between rays differs.
+// Root prepass: the root boxes of all meshes of the run (BVHTriMesh::Intersect,
+// bvhtrimesh.h:185-191) are first tested by the whole warp together against the ray's CURRENT
+// extent.  A root missed now is also missed later (ray.t only shrinks), so the walk proper
+// only enters the remaining candidates -- each lane on its own, in list order -- and repeats
+// the root test there when ray.t has shrunk since.  Per ray the sequence of box and triangle
+// tests is the reference's; the root tests just happen in lockstep instead of one loop step
+// each (a typical ray hits 1-2 of 5 roots).
 // `lane` is false for threads without a ray; they must still call (full-mask votes).
 template <bool ANY, bool COUNT, bool FAST>
 __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, float3 O, float3 D, float& rayT, HitRecord& hit,
@@ -89,23 +126,39 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
 	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
 		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
-	int mp = p0;                     // this lane's current mesh primitive
-	bool inside = false;             // walking mesh mp (else: about to enter it)
+	unsigned cand = 0;               // meshes of the run this lane still has to enter (bit m - p0)
+	unsigned bvhMask = 0;            // meshes of the run that have a root box
+	const float rayT0 = rayT;
+	for (int m = p0; m < p1; m++) {
+		const DMesh& mesh = sc.meshes[sc.prims[m].payload];
+		bool c = lane;
+		if (COUNT && mesh.nodes != nullptr) bvhMask |= 1u << (m - p0);
+		if (c && mesh.nodes != nullptr) {
+			NodeBox root = LoadNode(mesh.nodes, 0);
+			c = ExactBoxHit<FAST>(root.bmin, root.bmax, O, D, rD, filterOk, rayT0);
+		}
+		if (c) cand |= 1u << (m - p0);
+	}
+	int mp = p1 - 1;                 // this lane's current mesh primitive
+	bool inside = false;             // walking mesh mp (else: about to enter the next candidate)
 	const float4* nodes = nullptr;
 	const float4* tris = nullptr;
 	unsigned cur = 0;
 	int sp = 0;
 	bool active = lane;
-	while (__any_sync(0xffffffffu, active && mp < p1)) {
-		if (active && mp < p1) {
+	while (__any_sync(0xffffffffu, active && (inside || cand != 0u))) {
+		if (active && (inside || cand != 0u)) {
 			if (!inside) {
-				// enter mesh mp: root bounds test (BVHTriMesh::Intersect, bvhtrimesh.h:185-191)
+				// enter the next candidate mesh
+				int bit = __ffs((int)cand) - 1;
+				cand &= cand - 1u;
+				mp = p0 + bit;
 				const DMesh& mesh = sc.meshes[sc.prims[mp].payload];
 				nodes = mesh.nodes; tris = mesh.tris;
 				if (nodes == nullptr) {
 					// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
 					for (int j = 0; j < mesh.n_tris; j++) {
-						float4 a = __ldg(tris + 3 * j), b = __ldg(tris + 3 * j + 1), c = __ldg(tris + 3 * j + 2);
+						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
 						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
@@ -114,14 +167,13 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
 						}
 					}
-					mp++;
 				}
 				else {
 					NodeBox root = LoadNode(nodes, 0);
-					float dist;
-					if (COUNT) cnt.box_tests++;
-					if (BoundsIntersect(root.bmin, root.bmax, O, D, rayT, dist)) { cur = EncodeNode(0, root.first, root.count); sp = 0; inside = true; }
-					else mp++;
+					// ray.t unchanged since the prepass: same decision; else redo it with the shrunken extent
+					if (rayT == rayT0 || ExactBoxHit<FAST>(root.bmin, root.bmax, O, D, rD, filterOk, rayT)) {
+						cur = EncodeNode(0, root.first, root.count); sp = 0; inside = true;
+					}
 				}
 			}
 			else {
@@ -158,6 +210,13 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						pop = false;
 					}
 					else if (hl || hr) { cur = hl ? el : er; pop = false; }
+#if AGPT_PREFETCH_TRI
+					if (!pop && (cur & AGPT_ENT_LEAF1)) {
+						const float4* tp = tris + 3 * (int)(cur & 0x7fffffffu);
+						asm volatile("prefetch.global.L1 [%0];" :: "l"(tp));
+						asm volatile("prefetch.global.L1 [%0];" :: "l"(tp + 2));
+					}
+#endif
 				}
 				else {
 					int first, count;
@@ -167,7 +226,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						first = n.first; count = n.count;
 					}
 					for (int j = first; j < first + count; j++) {
-						float4 a = __ldg(tris + 3 * j), b = __ldg(tris + 3 * j + 1), c = __ldg(tris + 3 * j + 2);
+						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
 						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
@@ -178,7 +237,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 					}
 				}
 				if (pop) {
-					if (sp == 0) { inside = false; mp++; }
+					if (sp == 0) inside = false;
 					else {
 						sp--;
 						cur = (sp < AGPT_STACK_SMEM) ? stack[sp * stackStride] : local[sp - AGPT_STACK_SMEM];
@@ -187,6 +246,11 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 			}
 			if (ANY && found) active = false;
 		}
+	}
+	// one root test per mesh the reference reaches: all of the run, or up to the occluder (scene.h:15-19)
+	if (COUNT && lane) {
+		int last = ((ANY && found) ? mp : p1 - 1) - p0;
+		cnt.box_tests += (unsigned long long)__popc(bvhMask & (0xffffffffu >> (31 - last)));
 	}
 	return found;
 }
@@ -222,8 +286,8 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 			p++;
 		}
 		else {
-			int q = p + 1;                                     // run of consecutive mesh primitives
-			while (q < sc.n_prims && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
+			int q = p + 1;                                     // run of consecutive mesh primitives (<= 32 per call)
+			while (q < sc.n_prims && q < p + 32 && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
 			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
 			p = q;
 		}
