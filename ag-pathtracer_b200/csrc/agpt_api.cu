@@ -44,8 +44,6 @@ struct MeshStore {
 	void Free() { nodes.Free(); tris.Free(); normals.Free(); uvs.Free(); ids.Free(); }
 };
 
-static const int kWaveHistory = 64;
-
 struct agpt_ctx {
 	int device = 0;
 	cudaStream_t ownStream = nullptr, stream = nullptr;
@@ -88,6 +86,7 @@ struct agpt_ctx {
 	DevBuf<int> sortedShadow, sortedActive;
 	DevBuf<int> hist;             // AGPT_BUCKETS x { closest hist A/B, shadow hist A/B, offsets, running }
 	DevBuf<int> counts;           // 2 x 3
+	DevBuf<int> survivors, survivorCount;   // paths k_shade_b works on this wave
 	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned ring of kRing x 3 ints
@@ -98,9 +97,6 @@ struct agpt_ctx {
 	                              // every wave.  Measured slower (N=1: 133 vs 130.5 ms/step, N=8: 142.8 vs 139.3): the loose
 	                              // launch bounds and the extra empty wave cost more than the ~30 us sync gaps they remove.
 	bool overlapAny = true;       // AGPT_OVERLAP_ANY=0: any-hit trace on the main stream after the closest-hit trace
-	int shadeCompact = -1;        // AGPT_SHADE_COMPACT: 1 always, 0 never, -1 by the survival history below
-	float waveSurvival[kWaveHistory];   // share of wave w's shade entries that stayed active, last time seen (-1: never)
-	int shadeChunks = 8;          // AGPT_SHADE_CHUNKS: upper limit of 32-entry list pieces per shade warp
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
@@ -146,6 +142,7 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	CU(c->shadowKeys[0].Alloc(paths + slack)); CU(c->shadowKeys[1].Alloc(paths + slack)); CU(c->sortedShadow.Alloc(paths + slack));
 	CU(c->activeKeys[0].Alloc(paths + slack)); CU(c->activeKeys[1].Alloc(paths + slack)); CU(c->sortedActive.Alloc(paths + slack));
 	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths + slack));
+	CU(c->survivors.Alloc(paths + slack));
 	c->capacity = paths;
 	return AGPT_OK;
 }
@@ -225,6 +222,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
+	CU(c->survivorCount.Alloc(1));
 	CU(c->hist.Alloc(8 * AGPT_BUCKETS));
 	CU(c->traceCounters.Alloc(8));
 	CU(c->rayCounters.Alloc(1));
@@ -234,9 +232,6 @@ int agpt_create(int device, agpt_ctx** out) {
 	for (auto& e : c->ringEvents) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
-	for (float& v : c->waveSurvival) v = -1.f;
-	if (const char* e = getenv("AGPT_SHADE_COMPACT")) c->shadeCompact = atoi(e);
-	if (const char* e = getenv("AGPT_SHADE_CHUNKS")) c->shadeChunks = atoi(e) > 0 ? atoi(e) : 1;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_ACTIVE")) c->bucketActive = atoi(e) != 0;
 	*out = c;
@@ -258,6 +253,7 @@ int agpt_destroy(agpt_ctx* c) {
 	c->sortedClosest.Free(); c->keys[0].Free(); c->keys[1].Free(); c->hist.Free();
 	c->shadowKeys[0].Free(); c->shadowKeys[1].Free(); c->sortedShadow.Free();
 	c->activeKeys[0].Free(); c->activeKeys[1].Free(); c->sortedActive.Free();
+	c->survivors.Free(); c->survivorCount.Free();
 	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
 	for (auto& e : c->ringEvents) if (e) cudaEventDestroy(e);
@@ -282,7 +278,6 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	NEED(c != nullptr && n >= 0 && (n == 0 || meshes != nullptr), AGPT_ERR_INVALID, "bad mesh table");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
-	for (float& v : c->waveSurvival) v = -1.f;       // new scene: forget the per-wave survival history
 	for (auto& m : c->meshStore) m.Free();
 	c->meshStore.assign(n, MeshStore());
 	std::vector<DMesh> table(n);
@@ -365,7 +360,6 @@ int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
 	NEED(c != nullptr && cam != nullptr, AGPT_ERR_INVALID, "null camera");
 	c->cam = *cam;
 	c->haveCam = true;
-	for (float& v : c->waveSurvival) v = -1.f;
 	return AGPT_OK;
 }
 
@@ -475,7 +469,6 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	unsigned long long* cntAny = c->traceCounters.p + 4;
 
 	int ubClosest = n, ubShadow = 0, ubActive = n;   // upper bounds of the current wave's queue lengths
-	int shadedEntries[kRing] = {};                   // entries of the waves whose counts are still in flight
 	int cur = 0, wave = 0;
 	int ringHead = 0, ringTail = 0;                  // copies in flight: [ringTail, ringHead)
 	bool done = false;
@@ -533,26 +526,20 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
-		// Survivor compaction inside the shade blocks pays when a good part of the list is about to
-		// finish (open scenes: cfg 3 shade -22 %, cfg 4 -29 %); when most paths go on (closed rooms)
-		// its ring and barriers cost more than the denser warps save (cfg 5: +10 %).  How many
-		// entries of wave w stay active is almost the same from batch to batch of one scene, so the
-		// share seen the last time wave w was shaded decides; without history: compact.
-		const int wslot = wave < kWaveHistory ? wave : kWaveHistory - 1;
-		const bool compact = c->shadeCompact == 1 || (c->shadeCompact < 0 && (c->waveSurvival[wslot] < 0.f || c->waveSurvival[wslot] < 0.7f));
-		shadedEntries[wave % kRing] = ubActive;
-		int chunks = ubActive / (2 * c->smCount * AGPT_SHADE_THREADS);
-		chunks = chunks < 1 ? 1 : (chunks > c->shadeChunks ? c->shadeChunks : chunks);
-		sp.chunks = chunks;
-		const int shadeBlocks = Blocks(ubActive, AGPT_SHADE_THREADS * (compact ? chunks : 1));
+		// shade: k_shade_a (per active entry: NEE fold, emission, termination -> survivor list),
+		// then k_shade_b (per survivor: the BSDF work), blocks striding over the list
+		CU(cudaMemsetAsync(c->survivorCount.p, 0, sizeof(int), c->stream));
+		sp.count = c->survivorCount.p;
+		const int shadeBlocks = Blocks(ubActive, AGPT_SHADE_THREADS);      // upper bound: blocks past the survivor count return at once
 		if (c->envW > 0) {
-			if (compact) k_shade<true, true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
-			else k_shade<true, false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+			k_shade_a<true><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
+			k_shade_b<true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, c->survivors.p, q[cur ^ 1], sp, c->rayCounters.p);
 		}
 		else {
-			if (compact) k_shade<false, true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
-			else k_shade<false, false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, qin, q[cur ^ 1], sp, c->rayCounters.p);
+			k_shade_a<false><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
+			k_shade_b<false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, c->survivors.p, q[cur ^ 1], sp, c->rayCounters.p);
 		}
+		c->stats.kernel_launches++;
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
 		if (timing) CU(cudaEventRecord(c->evD, c->stream));
@@ -578,11 +565,6 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 			int landedWave = ringTail + 1;
 			ringTail++;
 			if (hc[2] == 0) { done = true; break; }
-			{
-				// wave `landedWave - 1` kept hc[2] of its entries active
-				int w = landedWave - 1, ent = shadedEntries[w % kRing];
-				if (ent > 0) c->waveSurvival[w < kWaveHistory ? w : kWaveHistory - 1] = (float)hc[2] / (float)ent;
-			}
 			if (landedWave == wave) { ubClosest = hc[0]; ubShadow = hc[1]; ubActive = hc[2]; }
 			else {
 				// older than the wave about to be launched: still bounds it

@@ -300,10 +300,9 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 
 // ---- shade -------------------------------------------------------------------------------
 struct ShadeParams {
-	const int* count;     // entries in q.active (this wave), on the device
+	const int* count;     // entries in the survivor list (this wave), on the device
 	int max_depth;
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
-	int chunks;           // 32-entry pieces of the active list per warp
 };
 
 __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
@@ -314,145 +313,121 @@ __device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
 
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
 //
-// Shape of the kernel.  Most entries of the active list need almost no work: their path left
+// Shade is two kernels.  Most entries of the active list need almost no work: their path left
 // the scene, hit max depth or only waited for its last next-event estimate (cfg 3, second wave:
 // 2 of 3).  Shading them in place would leave the expensive part -- light sampling and three
-// BSDF evaluations -- running on a third of each warp.  So a block is a producer/consumer: it
-// reads one entry per thread (phase A: fold the previous vertex's NEE, emission, termination),
-// pushes the SURVIVORS into a ring in shared memory, and whenever a full block's worth of them
-// is waiting (or the block's share of the list is exhausted) runs one dense round of the
-// phases B..E on them.
-//
+// BSDF evaluations -- running on a third of each warp.
+//   k_shade_a  one thread per active entry, small and memory-bound: folds the previous vertex's
+//              NEE into L, adds emission, finishes the paths that end here and appends the
+//              SURVIVORS (paths with a surface to shade) to a dense list;
+//   k_shade_b  one thread per survivor: phases B..E.
+// (A single kernel with the survivors compacted through a shared-memory ring was measured too:
+// per-block rings with two barriers per round -22 % shade on cfg 3 but +10 % in closed rooms;
+// per-warp rings without barriers desynchronise the warps and stall on instruction fetch.)
+template <bool ENV>
+__global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const int* __restrict__ active, const int* __restrict__ activeCount,
+		int* __restrict__ survivors, int* survivorCount, int max_depth) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int path = active[i];              // unconditional (allocation slack), overlaps with the count load
+	const bool valid = i < *activeCount;
+	if (!valid) path = 0;
+	bool survive = false;
+	if (valid) {
+		uint32_t flags = ps.flags[path];
+		const uint32_t flags0 = flags;
+		float4 h = ps.hitA[path];
+		float4 L4 = ps.L[path];
+		float3 L = f3(L4.x, L4.y, L4.z);
+		const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
+
+		// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
+		if (flags & (PF_NEE_SHADOW | PF_NEE_MIS)) {
+			float3 Ld = f3(0.f);
+			if ((flags & PF_NEE_SHADOW) && !ps.shadowOccluded[path]) {
+				float4 t = ps.neeLight[path];
+				Ld += f3(t.x, t.y, t.z);
+			}
+			if (flags & PF_NEE_MIS) {
+				float4 t = ps.neeMis[path];
+				int lightIdx = __float_as_int(t.w);
+				int misHit = ps.misPrim[path];
+				bool lit;
+				if (misHit >= 0) lit = sc.prims[misHit].area_light == lightIdx;            // lightIsect.shape->GetAreaLight() == &light
+				else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
+				if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
+			}
+			float4 nb = ps.neeBeta[path];
+			L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
+			flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
+		}
+
+		if (!(flags & PF_NO_CONTINUE)) {
+			// (2) the new vertex: did the ray hit, and is there emission to add (integrator.h:139-147)
+			int hitPrim = __float_as_int(h.w);
+			bool found = hitPrim >= 0;
+			int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
+			if (bounces == 0 || (flags & PF_SPECULAR)) {
+				float4 b4 = ps.beta[path];
+				float3 beta = f3(b4.x, b4.y, b4.z);
+				if (found) {
+					int al = sc.prims[hitPrim].area_light;
+					if (al >= 0) L += beta * f3(sc.lights[al].lemit);
+					else L += beta * f3(0.f);
+				}
+				else {
+					for (int l = 0; l < sc.n_lights; l++) {
+						if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
+						else if (ENV && sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) {
+							float4 d4 = ps.rayD[path];
+							L += beta * EnvLe(sc, f3(d4.x, d4.y, d4.z));
+						}
+					}
+				}
+			}
+			survive = found && bounces < max_depth;     // integrator.h:150
+		}
+		if (!survive) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);      // the path is complete
+		else {
+			ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
+			if (flags != flags0) ps.flags[path] = flags;
+		}
+	}
+	int slot = WarpAppend(survive, survivorCount);
+	if (survive) survivors[slot] = path;
+}
+
 // The kernel is ~100 KB of SASS (IEEE division / sqrt sequences, double-precision sincos), far
 // more than the instruction cache holds, so it matters that the resident warps walk the same
-// code at roughly the same time: one large block per SM whose warps start every round together
-// (two barriers per round, both in the cheap part).  Measured: per-warp rings without barriers
-// reach the same 18 of 32 threads per instruction but stall on instruction fetch instead
-// (6.0 "no instruction" cycles per issue against 0.4) and gain nothing.
+// code at roughly the same time: one large block per SM (measured, cfg 3 / cfg 5 shade ms per
+// 4 spp: 128-thread blocks 11.5 / 22.4, 512-thread blocks 9.9 / 20.9; 768 threads at 80
+// registers another -7 % / -3 %).
 #ifndef AGPT_SHADE_THREADS
 #define AGPT_SHADE_THREADS 768
 #endif
-#define AGPT_SHADE_RING (2 * AGPT_SHADE_THREADS - 1)     // fewer than THREADS waiting + at most THREADS pushed
 
-template <bool ENV, bool COMPACT>
-__global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade(DScene sc, PathState ps, WaveQueues qin, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
-	// survivors of phase A: {path, flags, L.x, L.y} and {L.z, beta.xyz}
-	__shared__ float4 ringA[COMPACT ? AGPT_SHADE_RING : 1];
-	__shared__ float4 ringB[COMPACT ? AGPT_SHADE_RING : 1];
-	__shared__ int ringTail;                                                // entries ever pushed
+template <bool ENV>
+__global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
-	const unsigned lanesBelow = (1u << lane) - 1u;
 	const int count = *sp.count;
-	const int chunks = COMPACT ? sp.chunks : 1;
-	int base = blockIdx.x * AGPT_SHADE_THREADS * chunks;                    // this block's share of the active list
-	const int end = min(base + AGPT_SHADE_THREADS * chunks, count);
-	int head = 0;                                                           // entries ever popped (block-uniform)
 	int nExtend = 0, nMis = 0, nShadow = 0, nSkip = 0, nMisCulled = 0, nTailCulled = 0;   // ray statistics (warp-uniform)
-	const float lightSelPdf = sc.n_lights > 0 ? 1.f / sc.n_lights : 0.f;
-	if (COMPACT) {
-		if (threadIdx.x == 0) ringTail = 0;
-		__syncthreads();
-	}
 
-	while (true) {
-		// ================= phase A: previous vertex's NEE, emission, termination =================
-		bool survive = false;
+	// one block-sized piece of the list per block, no loop: warps that start together stay together
+	for (int base = blockIdx.x * AGPT_SHADE_THREADS; base < count; base = count) {
+		const int i = base + threadIdx.x;
+		const bool valid = i < count;
 		int path = 0;
 		uint32_t flags = 0;
-		float3 L = f3(0.f), beta = f3(0.f);
+		float3 beta = f3(0.f);
 		float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, h = o4;
-		if (base < end) {
-			const int i = base + threadIdx.x;
-			if (i < end) {
-				path = qin.active[i];
-				flags = ps.flags[path];
-				h = ps.hitA[path];
-				if (!COMPACT || ENV) d4 = ps.rayD[path];
-				if (!COMPACT) o4 = ps.rayO[path];          // (a compacted survivor fetches its ray in its dense round)
-				float4 L4 = ps.L[path];
-				L = f3(L4.x, L4.y, L4.z);
-				float4 b4 = ps.beta[path];
-				beta = f3(b4.x, b4.y, b4.z);
-
-				// (1) fold in the next-event estimate of the previous vertex (integrator.h:53-58,80-88,104,166)
-				if (flags & (PF_NEE_SHADOW | PF_NEE_MIS)) {
-					float3 Ld = f3(0.f);
-					if ((flags & PF_NEE_SHADOW) && !ps.shadowOccluded[path]) {
-						float4 t = ps.neeLight[path];
-						Ld += f3(t.x, t.y, t.z);
-					}
-					if (flags & PF_NEE_MIS) {
-						float4 t = ps.neeMis[path];
-						int lightIdx = __float_as_int(t.w);
-						int misHit = ps.misPrim[path];
-						bool lit;
-						if (misHit >= 0) lit = sc.prims[misHit].area_light == lightIdx;            // lightIsect.shape->GetAreaLight() == &light
-						else lit = sc.lights[lightIdx].type != AGPT_LIGHT_AREA;                 // light.Le(ray): only infinite lights emit
-						if (lit) Ld += f3(t.x, t.y, t.z);      // the term already carries Li (a black Li adds zero, like upstream's skip)
-					}
-					float4 nb = ps.neeBeta[path];
-					L += f3(nb.x, nb.y, nb.z) * (Ld / lightSelPdf);
-					flags &= ~(PF_NEE_SHADOW | PF_NEE_MIS);
-				}
-
-				if (!(flags & PF_NO_CONTINUE)) {
-					// (2) the new vertex: did the ray hit, and is there emission to add (integrator.h:139-147)
-					int hitPrim = __float_as_int(h.w);
-					bool found = hitPrim >= 0;
-					int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
-					if (bounces == 0 || (flags & PF_SPECULAR)) {
-						if (found) {
-							int al = sc.prims[hitPrim].area_light;
-							if (al >= 0) L += beta * f3(sc.lights[al].lemit);
-							else L += beta * f3(0.f);
-						}
-						else {
-							for (int l = 0; l < sc.n_lights; l++) {
-								if (sc.lights[l].type == AGPT_LIGHT_UNIFORM_INFINITE) L += beta * f3(sc.lights[l].lemit);
-								else if (ENV && sc.lights[l].type == AGPT_LIGHT_INFINITE_AREA) L += beta * EnvLe(sc, f3(d4.x, d4.y, d4.z));
-							}
-						}
-					}
-					survive = found && bounces < sp.max_depth;     // integrator.h:150
-				}
-				if (!survive) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);      // the path is complete
-			}
-			base += AGPT_SHADE_THREADS;
+		if (valid) {
+			path = survivors[i];
+			flags = ps.flags[path];
+			o4 = ps.rayO[path]; d4 = ps.rayD[path]; h = ps.hitA[path];
+			float4 b4 = ps.beta[path];
+			beta = f3(b4.x, b4.y, b4.z);
 		}
-
-		bool valid = survive;
-		if (COMPACT) {
-			// push the survivors, then pop one dense round as soon as a block's worth is waiting
-			const unsigned m = __ballot_sync(0xffffffffu, survive);
-			int slot0 = 0;
-			if (lane == 0 && m) slot0 = atomicAdd(&ringTail, __popc(m));
-			slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-			if (survive) {
-				int s = (slot0 + __popc(m & lanesBelow)) % AGPT_SHADE_RING;
-				ringA[s] = make_float4(__int_as_float(path), __uint_as_float(flags), L.x, L.y);
-				ringB[s] = make_float4(L.z, beta.x, beta.y, beta.z);
-			}
-			__syncthreads();
-			const int pending = ringTail - head;
-			if (base < end && pending < AGPT_SHADE_THREADS) { __syncthreads(); continue; }     // keep collecting
-			if (pending == 0) break;
-			const int nRound = min(pending, AGPT_SHADE_THREADS);
-			valid = (int)threadIdx.x < nRound;
-			if (valid) {
-				int s = (head + (int)threadIdx.x) % AGPT_SHADE_RING;
-				float4 a = ringA[s], b = ringB[s];
-				path = __float_as_int(a.x); flags = __float_as_uint(a.y);
-				L = f3(a.z, a.w, b.x);
-				beta = f3(b.y, b.z, b.w);
-			}
-			head += nRound;
-			__syncthreads();                   // records are in registers: the next phase A may push again
-			if (!__any_sync(0xffffffffu, valid)) continue;
-			if (valid) { o4 = ps.rayO[path]; d4 = ps.rayD[path]; h = ps.hitA[path]; }
-		}
-
-		// ================= one dense round: phases B..E for the survivors =================
 		const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
+
 		bool emitExtend = false, emitShadow = false, emitMis = false, stayActive = false, skipRay = false, misCulled = false, tailCulled = false;
 		int keyExtend = 0, keyMis = 0, keyShadow = 0;
 		bool finished = false, full = false;
@@ -690,9 +665,8 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade(DScene sc, Path
 			if (emitMis) flags |= PF_NEE_MIS;
 		}
 		if (valid) {
-			ps.L[path] = make_float4(L.x, L.y, L.z, 0.f);
 			ps.flags[path] = flags;
-			if (finished) ps.Lout[path] = make_float4(L.x, L.y, L.z, 0.f);
+			if (finished) { float4 Lf = ps.L[path]; ps.Lout[path] = Lf; }       // L was completed by k_shade_a; nothing is added here
 		}
 
 		// (5) queue the next wave: one atomic per warp per queue
@@ -716,7 +690,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade(DScene sc, Path
 		nSkip += __popc(__ballot_sync(0xffffffffu, skipRay));
 		nMisCulled += __popc(__ballot_sync(0xffffffffu, misCulled));
 		nTailCulled += __popc(__ballot_sync(0xffffffffu, tailCulled));
-		if (!COMPACT) break;
 	}
 
 	// ray statistics: one atomic per counter per warp
