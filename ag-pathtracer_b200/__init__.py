@@ -8,5 +8,5 @@ a hyphen, so tests and bench load this package through ``importlib`` under the m
 """
 from .binding import (AgptError, Context, HostScene, HostTracer, Material, Stats, FLAG_COUNTERS, FLAG_TIMING,  # noqa: F401
                       FLAG_STRICT_BOXES, MAT_DISNEY, MAT_MIRROR, HIT_DTYPE, config_defaults, core, device_count, host,
-                      lib_paths, make_material, pinned_film)
+                      lib_paths, make_material, pinned_film, set_build_options, get_build_options)
 from . import multigpu  # noqa: F401,E402

@@ -277,6 +277,18 @@ def make_material(mtype, color, roughness=0.0, metallic=0.0):
     return m
 
 
+def set_build_options(threads=0, cache_dir=None):
+    """BVH builder threads (>= 1) and cache directory ('' = off) of the host mirror."""
+    _check(host().agpt_host_set_build_options(c_int(threads), None if cache_dir is None else str(cache_dir).encode()), host_side=True)
+
+
+def get_build_options():
+    t = c_int()
+    buf = ctypes.create_string_buffer(4096)
+    _check(host().agpt_host_get_build_options(byref(t), buf, c_int(4096)), host_side=True)
+    return t.value, buf.value.decode()
+
+
 def config_defaults(config):
     out = (c_int * 5)()
     name = c_char_p()

@@ -173,6 +173,20 @@ int agpt_host_make_material(int type, const float* c, float roughness, float met
 	return AGPT_OK;
 }
 
+int agpt_host_set_build_options(int threads, const char* cache_dir) {
+	BVHTriMesh::BuildOptions& opt = BVHTriMesh::Options();
+	if (threads >= 1) opt.threads = threads;
+	if (cache_dir) opt.cacheDir = cache_dir;
+	return AGPT_OK;
+}
+
+int agpt_host_get_build_options(int* threads, char* cache_dir, int cache_dir_capacity) {
+	const BVHTriMesh::BuildOptions& opt = BVHTriMesh::Options();
+	if (threads) *threads = opt.threads;
+	if (cache_dir && cache_dir_capacity > 0) snprintf(cache_dir, (size_t)cache_dir_capacity, "%s", opt.cacheDir.c_str());
+	return AGPT_OK;
+}
+
 int agpt_host_tracer_create(int max_depth, int device, agpt_host_tracer** out) {
 	if (!out) return HostFail("null out");
 	*out = nullptr;

@@ -58,6 +58,15 @@ int agpt_host_material_export(agpt_host_scene* scene, int prim, float* out20);
 /* DisneyMaterial(color, roughness, metallic) / MirrorMaterial(color) -> device record */
 int agpt_host_make_material(int type, const float* color3, float roughness, float metallic, agpt_material* out);
 
+/* BVH build settings of the host mirror (reference: BuildRecursive +
+ * FlattenBVHTree, bvhtrimesh.h:213-330, single-threaded and uncached upstream).
+ * threads >= 1 sets the number of builder threads (default: AGPT_BUILD_THREADS, else the
+ * hardware concurrency capped at 16); cache_dir != NULL sets the directory flattened BVHs are
+ * cached in, "" turns the cache off (default: AGPT_BVH_CACHE_DIR, else off).  The arrays are
+ * byte-identical whatever the settings. */
+int agpt_host_set_build_options(int threads, const char* cache_dir);
+int agpt_host_get_build_options(int* threads, char* cache_dir, int cache_dir_capacity);
+
 /* CudaPathTracer(max_depth, device) */
 int agpt_host_tracer_create(int max_depth, int device, agpt_host_tracer** out);
 int agpt_host_tracer_destroy(agpt_host_tracer* tracer);

@@ -66,3 +66,55 @@ def test_bvh_layout_invariants(agpt):
     assert count[leaves].sum() == len(order) == 20 * 4 ** 4
     assert sorted(order.tolist()) == list(range(len(order)))
     assert len(nodes) == 2 * len(order) - 1 + 1
+
+
+def _all_bvhs(hs):
+    out = []
+    for p in range(hs.counts()["prims"]):
+        if hs.prim_info(p)["kind"] == 2:
+            out.append(hs.bvh(p))
+    return out
+
+
+def test_parallel_build_equals_serial_build(agpt):
+    """forking the top of the SAH build must not change one byte of the arrays
+    (large enough that the builder really forks: > 4096 triangles per range)."""
+    threads0, cache0 = agpt.get_build_options()
+    try:
+        agpt.set_build_options(1, "")
+        serial = _all_bvhs(agpt.HostScene(2, 7))
+        for t in (2, 5, 16):
+            agpt.set_build_options(t, "")
+            par = _all_bvhs(agpt.HostScene(2, 7))
+            assert len(par) == len(serial) > 0
+            for (n0, o0), (n1, o1) in zip(serial, par):
+                assert n0.shape == n1.shape and np.array_equal(n0, n1) and np.array_equal(o0, o1), f"{t} threads"
+    finally:
+        agpt.set_build_options(threads0, cache0)
+
+
+def test_bvh_cache_round_trip_and_damage(agpt, tmp_path):
+    threads0, cache0 = agpt.get_build_options()
+    try:
+        agpt.set_build_options(0, "")
+        fresh = _all_bvhs(agpt.HostScene(3, 4))
+        agpt.set_build_options(0, str(tmp_path))
+        assert agpt.get_build_options()[1] == str(tmp_path)
+        built = _all_bvhs(agpt.HostScene(3, 4))              # builds and writes the cache files
+        files = sorted(tmp_path.glob("*.agbvh"))
+        assert len(files) >= 1 and not list(tmp_path.glob("*.tmp*"))
+        cached = _all_bvhs(agpt.HostScene(3, 4))             # reads them back
+        for (n0, o0), (n1, o1), (n2, o2) in zip(fresh, built, cached):
+            assert np.array_equal(n0, n1) and np.array_equal(o0, o1)
+            assert np.array_equal(n0, n2) and np.array_equal(o0, o2)
+        # a truncated and a bit-flipped-header file are rejected and rebuilt, never trusted
+        data = files[0].read_bytes()
+        files[0].write_bytes(data[: len(data) // 2])
+        if len(files) > 1:
+            d1 = bytearray(files[1].read_bytes()); d1[9] ^= 0xFF; files[1].write_bytes(bytes(d1))
+        again = _all_bvhs(agpt.HostScene(3, 4))
+        for (n0, o0), (n1, o1) in zip(fresh, again):
+            assert np.array_equal(n0, n1) and np.array_equal(o0, o1)
+        assert files[0].stat().st_size == len(data)          # and the damaged file was replaced
+    finally:
+        agpt.set_build_options(threads0, cache0)
