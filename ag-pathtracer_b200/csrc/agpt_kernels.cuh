@@ -405,6 +405,15 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 #define AGPT_SHADE_THREADS 768
 #endif
 
+#ifndef AGPT_SHADE_PHASE_SYNC
+#define AGPT_SHADE_PHASE_SYNC 0      // block barrier before each phase (every thread of a block reaches them)
+#endif
+#if AGPT_SHADE_PHASE_SYNC
+#define SHADE_PHASE_BARRIER() __syncthreads()
+#else
+#define SHADE_PHASE_BARRIER() ((void)0)
+#endif
+
 template <bool ENV>
 __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
@@ -456,6 +465,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 			else { full = true; mat = sc.mats + prim.material; }
 		}
 
+		SHADE_PHASE_BARRIER();
 		// ================= phase B: BSDF frame, random numbers, light sample =================
 		const float3 wo = -D;
 		VertexBsdf vb;
@@ -529,6 +539,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 		}
 		const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
 
+		SHADE_PHASE_BARRIER();
 		// ================= phase C: sample the MIS and the continuation directions =================
 		DirSample smp[2];
 	#pragma unroll 1
@@ -538,6 +549,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 			else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
 		}
 
+		SHADE_PHASE_BARRIER();
 		// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
 		float3 fDir[3];
 		float pdfDir[3];
@@ -570,6 +582,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 			}
 			}
 
+		SHADE_PHASE_BARRIER();
 		// ================= phase E: EstimateDirect terms, throughput, next rays =================
 		if (full) {
 			// (3) EstimateDirect (integrator.h:38-93)

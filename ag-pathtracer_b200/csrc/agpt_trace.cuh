@@ -94,6 +94,9 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 	return BoundsIntersect(bmin, bmax, O, D, rayT, dist);
 }
 
+#ifndef AGPT_ANY_NEAR_FIRST
+#define AGPT_ANY_NEAR_FIRST 1
+#endif
 #ifndef AGPT_PREFETCH_TRI
 #define AGPT_PREFETCH_TRI 0      // prefetch the triangle of a single-triangle leaf as soon as the walk decides to visit it next
 #endif
@@ -190,9 +193,19 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						SlabApprox(l.bmin, l.bmax, O, rD, rayT, dl, xl);
 						SlabApprox(r.bmin, r.bmax, O, rD, rayT, dr, xr);
 						int cl = SlabDecision(dl, xl), cr = SlabDecision(dr, xr);
-						int cs = (ANY || cl != 1 || cr != 1) ? 0 : NearerDecision(dl, dr);
-						hl = cl == 1; hr = cr == 1; swapKids = cs == 1;
-						strict = (cl | cr | cs) < 0;       // some comparison fell inside the guard band
+						if (ANY && !COUNT && AGPT_ANY_NEAR_FIRST) {
+							// Occlusion does not depend on the order of the walk (upstream: left first,
+							// bvhtrimesh.h:400-411), nor on visiting a box that a borderline test would
+							// have skipped: nearer child first finds occluders sooner, and a comparison
+							// inside the guard band simply counts as a hit.  The counting instantiation
+							// keeps upstream's order so its visit counts stay comparable.
+							hl = cl != 0; hr = cr != 0; swapKids = dr < dl;
+						}
+						else {
+							int cs = (ANY || cl != 1 || cr != 1) ? 0 : NearerDecision(dl, dr);
+							hl = cl == 1; hr = cr == 1; swapKids = cs == 1;
+							strict = (cl | cr | cs) < 0;       // some comparison fell inside the guard band
+						}
 					}
 					if (strict) {
 						hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
