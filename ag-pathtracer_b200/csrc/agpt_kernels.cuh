@@ -333,6 +333,8 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 	if (!valid) path = 0;
 	bool survive = false;
 	if (valid) {
+		// (loading the NEE terms unconditionally, to save the dependent round trip, measured slower:
+		// the kernel then moves ~60 B more per entry and it is those bytes that cost)
 		uint32_t flags = ps.flags[path];
 		const uint32_t flags0 = flags;
 		float4 h = ps.hitA[path];
@@ -392,8 +394,21 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 			if (flags != flags0) ps.flags[path] = flags;
 		}
 	}
-	int slot = WarpAppend(survive, survivorCount);
-	if (survive) survivors[slot] = path;
+	// append the survivors: one atomic per BLOCK (a million same-address atomics per launch, one
+	// per warp, are what the kernel would otherwise wait for), order inside the block kept
+	__shared__ int warpBase[8];
+	__shared__ int blockBase;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned m = __ballot_sync(0xffffffffu, survive);
+	if (lane == 0) warpBase[warp] = __popc(m);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int total = 0;
+		for (int w = 0; w < 8; w++) { int c = warpBase[w]; warpBase[w] = total; total += c; }
+		blockBase = total ? atomicAdd(survivorCount, total) : 0;
+	}
+	__syncthreads();
+	if (survive) survivors[blockBase + warpBase[warp] + __popc(m & ((1u << lane) - 1u))] = path;
 }
 
 // The kernel is ~100 KB of SASS (IEEE division / sqrt sequences, double-precision sincos), far
@@ -418,8 +433,6 @@ template <bool ENV>
 __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
 	const int count = *sp.count;
-	int nExtend = 0, nMis = 0, nShadow = 0, nSkip = 0, nMisCulled = 0, nTailCulled = 0;   // ray statistics (warp-uniform)
-
 	// one block-sized piece of the list per block, no loop: warps that start together stay together
 	for (int base = blockIdx.x * AGPT_SHADE_THREADS; base < count; base = count) {
 		const int i = base + threadIdx.x;
@@ -428,11 +441,14 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 		uint32_t flags = 0;
 		float3 beta = f3(0.f);
 		float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = o4, h = o4;
+		int hitSlot = 0;
+		uint32_t rng = 0;
 		if (valid) {
 			path = survivors[i];
 			flags = ps.flags[path];
 			o4 = ps.rayO[path]; d4 = ps.rayD[path]; h = ps.hitA[path];
 			float4 b4 = ps.beta[path];
+			hitSlot = ps.hitSlot[path]; rng = ps.rng[path];        // (requested now: one round trip for all per-path state)
 			beta = f3(b4.x, b4.y, b4.z);
 		}
 		const float3 O = f3(o4.x, o4.y, o4.z), D = f3(d4.x, d4.y, d4.z);
@@ -452,7 +468,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 			// SurfaceInteraction of the closest hit
 			if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
 			else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
-			else TriangleSurface(sc.meshes[prim.payload], ps.hitSlot[path], O, D, h.x, h.y, h.z, si);
+			else TriangleSurface(sc.meshes[prim.payload], hitSlot, O, D, h.x, h.y, h.z, si);
 
 			if (prim.material < 0) {
 				// null material: pass straight through, bounce count unchanged (integrator.h:152-161)
@@ -469,7 +485,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 		// ================= phase B: BSDF frame, random numbers, light sample =================
 		const float3 wo = -D;
 		VertexBsdf vb;
-		uint32_t rng = 0;
 		bool doNee = false;
 		int numLight = 0;
 		float2 uLight = make_float2(0, 0), uScattering = make_float2(0, 0), u = make_float2(0, 0);
@@ -480,7 +495,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 		int lightType = -1, lightPrimType = -1, lightPayload = 0;
 		VertexBsdfInit(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
 		if (full) {
-			rng = ps.rng[path];
 			doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
 			// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
 			// UniformSampleOneLight (integrator.h:95-105): light pick, uLight, uScattering
@@ -682,37 +696,62 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 			if (finished) { float4 Lf = ps.L[path]; ps.Lout[path] = Lf; }       // L was completed by k_shade_a; nothing is added here
 		}
 
-		// (5) queue the next wave: one atomic per warp per queue
-		int slot = WarpAppend(emitExtend, qout.counts + 0);
-		if (emitExtend) { qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
+		// (5) queue the next wave.  One atomic per queue per BLOCK: the counters are single
+		// addresses, and one atomic per warp (a million a launch) serialises in L2 -- measured
+		// on k_shade_a: -3 ms per step from this alone.  Every thread of the block gets here.
+		__shared__ int warpCount[AGPT_SHADE_THREADS / 32][4];      // extend, MIS, shadow, active; then: offsets
+		__shared__ int queueBase[3];
+		__shared__ int blockStats[6];
+		const int warp = threadIdx.x >> 5;
+		const unsigned below = (1u << lane) - 1u;
+		const unsigned mE = __ballot_sync(0xffffffffu, emitExtend), mM = __ballot_sync(0xffffffffu, emitMis);
+		const unsigned mS = __ballot_sync(0xffffffffu, emitShadow), mA = __ballot_sync(0xffffffffu, stayActive);
+		if (threadIdx.x < 6) blockStats[threadIdx.x] = 0;
+		if (lane == 0) { warpCount[warp][0] = __popc(mE); warpCount[warp][1] = __popc(mM); warpCount[warp][2] = __popc(mS); warpCount[warp][3] = __popc(mA); }
+		__syncthreads();
+		if (threadIdx.x < 3) {
+			// thread 0: closest queue (a warp's path rays, then its MIS rays), 1: shadow queue, 2: active list
+			int total = 0;
+			for (int w = 0; w < AGPT_SHADE_THREADS / 32; w++) {
+				if (threadIdx.x == 0) {
+					int c0 = warpCount[w][0], c1 = warpCount[w][1];
+					warpCount[w][0] = total; total += c0;
+					warpCount[w][1] = total; total += c1;
+				}
+				else {
+					int c = warpCount[w][threadIdx.x + 1];
+					warpCount[w][threadIdx.x + 1] = total; total += c;
+				}
+			}
+			queueBase[threadIdx.x] = total ? atomicAdd(qout.counts + threadIdx.x, total) : 0;
+		}
+		// ray statistics, first into the block's counters
+		const unsigned mSkip = __ballot_sync(0xffffffffu, skipRay), mMc = __ballot_sync(0xffffffffu, misCulled), mTc = __ballot_sync(0xffffffffu, tailCulled);
+		if (lane == 0) {
+			if (mE) atomicAdd(&blockStats[0], __popc(mE));
+			if (mM) atomicAdd(&blockStats[1], __popc(mM));
+			if (mS) atomicAdd(&blockStats[2], __popc(mS));
+			if (mSkip) atomicAdd(&blockStats[3], __popc(mSkip));
+			if (mMc) atomicAdd(&blockStats[4], __popc(mMc));
+			if (mTc) atomicAdd(&blockStats[5], __popc(mTc));
+		}
+		__syncthreads();
+		if (emitExtend) { int slot = queueBase[0] + warpCount[warp][0] + __popc(mE & below); qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
 		WarpHistAdd(emitExtend, keyExtend, qout.hist);
-		slot = WarpAppend(emitMis, qout.counts + 0);
-		if (emitMis) { qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
+		if (emitMis) { int slot = queueBase[0] + warpCount[warp][1] + __popc(mM & below); qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
 		WarpHistAdd(emitMis, keyMis, qout.hist);
-		slot = WarpAppend(emitShadow, qout.counts + 1);
-		if (emitShadow) { qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
+		if (emitShadow) { int slot = queueBase[1] + warpCount[warp][2] + __popc(mS & below); qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
 		WarpHistAdd(emitShadow, keyShadow, qout.shadowHist);
-		slot = WarpAppend(stayActive, qout.counts + 2);
 		int keyActive = emitExtend ? keyExtend : 0;      // paths that only wait for their NEE go to bucket 0
-		if (stayActive) { qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
+		if (stayActive) { int slot = queueBase[2] + warpCount[warp][3] + __popc(mA & below); qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
 		WarpHistAdd(stayActive, keyActive, qout.activeHist);
 
-		nExtend += __popc(__ballot_sync(0xffffffffu, emitExtend));
-		nMis += __popc(__ballot_sync(0xffffffffu, emitMis));
-		nShadow += __popc(__ballot_sync(0xffffffffu, emitShadow));
-		nSkip += __popc(__ballot_sync(0xffffffffu, skipRay));
-		nMisCulled += __popc(__ballot_sync(0xffffffffu, misCulled));
-		nTailCulled += __popc(__ballot_sync(0xffffffffu, tailCulled));
-	}
-
-	// ray statistics: one atomic per counter per warp
-	if (lane == 0) {
-		if (nExtend) atomicAdd(&rc->rays_closest, (unsigned long long)nExtend);
-		if (nMis) atomicAdd(&rc->rays_mis, (unsigned long long)nMis);
-		if (nShadow) atomicAdd(&rc->rays_shadow, (unsigned long long)nShadow);
-		if (nSkip) atomicAdd(&rc->rays_skip, (unsigned long long)nSkip);
-		if (nMisCulled) atomicAdd(&rc->rays_mis_culled, (unsigned long long)nMisCulled);
-		if (nTailCulled) atomicAdd(&rc->rays_tail_culled, (unsigned long long)nTailCulled);
+		// ray statistics: one atomic per counter per block
+		if (threadIdx.x < 6 && blockStats[threadIdx.x]) {
+			unsigned long long* dst = threadIdx.x == 0 ? &rc->rays_closest : threadIdx.x == 1 ? &rc->rays_mis : threadIdx.x == 2 ? &rc->rays_shadow :
+				threadIdx.x == 3 ? &rc->rays_skip : threadIdx.x == 4 ? &rc->rays_mis_culled : &rc->rays_tail_culled;
+			atomicAdd(dst, (unsigned long long)blockStats[threadIdx.x]);
+		}
 	}
 }
 
