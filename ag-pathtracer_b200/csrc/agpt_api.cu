@@ -82,9 +82,9 @@ struct agpt_ctx {
 	DevBuf<uint32_t> u32[2];
 	DevBuf<int> queues[6];        // closest A/B (2*cap), shadow A/B, active A/B
 	DevBuf<int> sortedClosest;    // closest queue in bucket order (2*cap)
-	DevBuf<unsigned short> keys[2], shadowKeys[2], activeKeys[2];
-	DevBuf<int> sortedShadow, sortedActive;
-	DevBuf<int> hist;             // AGPT_BUCKETS x { closest hist A/B, shadow hist A/B, offsets, running }
+	DevBuf<unsigned short> keys[2], shadowKeys[2];
+	DevBuf<int> sortedShadow;
+	DevBuf<int> hist;             // AGPT_BUCKETS x { histogram, offsets, running }
 	DevBuf<int> counts;           // 2 x 3
 	DevBuf<int> survivors, survivorCount;   // paths k_shade_b works on this wave
 	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
@@ -98,7 +98,6 @@ struct agpt_ctx {
 	                              // launch bounds and the extra empty wave cost more than the ~30 us sync gaps they remove.
 	bool overlapAny = true;       // AGPT_OVERLAP_ANY=0: any-hit trace on the main stream after the closest-hit trace
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
-	bool bucketActive = false;    // ... and on the shade list (AGPT_BUCKET_ACTIVE=1): helps multi-material scenes (cfg 3/4: -10 % shade), hurts single-material ones (cfg 5: +30 %)
 };
 
 #ifndef AGPT_BATCH_LOG2
@@ -140,7 +139,6 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	CU(c->queues[0].Alloc(2 * paths + slack)); CU(c->queues[1].Alloc(2 * paths + slack));
 	CU(c->sortedClosest.Alloc(2 * paths + slack)); CU(c->keys[0].Alloc(2 * paths + slack)); CU(c->keys[1].Alloc(2 * paths + slack));
 	CU(c->shadowKeys[0].Alloc(paths + slack)); CU(c->shadowKeys[1].Alloc(paths + slack)); CU(c->sortedShadow.Alloc(paths + slack));
-	CU(c->activeKeys[0].Alloc(paths + slack)); CU(c->activeKeys[1].Alloc(paths + slack)); CU(c->sortedActive.Alloc(paths + slack));
 	for (int k = 2; k < 6; k++) CU(c->queues[k].Alloc(paths + slack));
 	CU(c->survivors.Alloc(paths + slack));
 	c->capacity = paths;
@@ -223,7 +221,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(c->counts.Alloc(6));
 	CU(c->survivorCount.Alloc(1));
-	CU(c->hist.Alloc(8 * AGPT_BUCKETS));
+	CU(c->hist.Alloc(3 * AGPT_BUCKETS));
 	CU(c->traceCounters.Alloc(8));
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
@@ -233,7 +231,6 @@ int agpt_create(int device, agpt_ctx** out) {
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
-	if (const char* e = getenv("AGPT_BUCKET_ACTIVE")) c->bucketActive = atoi(e) != 0;
 	*out = c;
 	return AGPT_OK;
 }
@@ -252,7 +249,6 @@ int agpt_destroy(agpt_ctx* c) {
 	for (auto& b : c->queues) b.Free();
 	c->sortedClosest.Free(); c->keys[0].Free(); c->keys[1].Free(); c->hist.Free();
 	c->shadowKeys[0].Free(); c->shadowKeys[1].Free(); c->sortedShadow.Free();
-	c->activeKeys[0].Free(); c->activeKeys[1].Free(); c->sortedActive.Free();
 	c->survivors.Free(); c->survivorCount.Free();
 	c->counts.Free(); c->traceCounters.Free(); c->rayCounters.Free();
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
@@ -456,13 +452,12 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 	for (int k = 0; k < 2; k++) {
 		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
 		q[k].counts = c->counts.p + 3 * k;
-		q[k].keys = c->keys[k].p; q[k].hist = c->hist.p + AGPT_BUCKETS * k;
-		q[k].shadowKeys = c->shadowKeys[k].p; q[k].shadowHist = c->hist.p + AGPT_BUCKETS * (2 + k);
-		q[k].activeKeys = c->activeKeys[k].p; q[k].activeHist = c->hist.p + AGPT_BUCKETS * (4 + k);
+		q[k].keys = c->keys[k].p; q[k].shadowKeys = c->shadowKeys[k].p;
 	}
-	int* bucketOffsets = c->hist.p + 6 * AGPT_BUCKETS;
-	int* bucketRunning = c->hist.p + 7 * AGPT_BUCKETS;
-	const bool bucketing = c->bucketRays, bucketActive = c->bucketActive;
+	int* bucketHist = c->hist.p;
+	int* bucketOffsets = c->hist.p + AGPT_BUCKETS;
+	int* bucketRunning = c->hist.p + 2 * AGPT_BUCKETS;
+	const bool bucketing = c->bucketRays;
 	const bool overlap = c->overlapAny && !timing;
 	float msClosest = 0, msAny = 0, msShade = 0;
 	unsigned long long* cntClosest = c->traceCounters.p;
@@ -479,23 +474,22 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		WaveQueues qin = q[cur];
 		if (wave > 0 && bucketing) {
 			// bucket pass: rays that start in the same cell going the same way end up adjacent
+			const int perBlock = 256 * AGPT_BUCKET_ITEMS;
 			if (ubClosest > 0) {
-				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].hist, bucketOffsets, bucketRunning);
-				k_bucket_scatter<<<Blocks(ubClosest, 256), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, q[cur].counts + 0, bucketOffsets, bucketRunning, c->sortedClosest.p);
-				c->stats.kernel_launches += 2;
+				CU(cudaMemsetAsync(bucketHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+				k_bucket_hist<<<Blocks(ubClosest, perBlock), 256, 0, c->stream>>>(q[cur].keys, q[cur].counts + 0, bucketHist);
+				k_bucket_scan<<<1, 1024, 0, c->stream>>>(bucketHist, bucketOffsets, bucketRunning);
+				k_bucket_scatter<<<Blocks(ubClosest, perBlock), 256, 0, c->stream>>>(q[cur].closest, q[cur].keys, q[cur].counts + 0, bucketOffsets, bucketRunning, c->sortedClosest.p);
+				c->stats.kernel_launches += 3;
 				closestQueue = c->sortedClosest.p;
 			}
 			if (ubShadow > 0) {
-				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].shadowHist, bucketOffsets, bucketRunning);
-				k_bucket_scatter<<<Blocks(ubShadow, 256), 256, 0, c->stream>>>(q[cur].shadow, q[cur].shadowKeys, q[cur].counts + 1, bucketOffsets, bucketRunning, c->sortedShadow.p);
-				c->stats.kernel_launches += 2;
+				CU(cudaMemsetAsync(bucketHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
+				k_bucket_hist<<<Blocks(ubShadow, perBlock), 256, 0, c->stream>>>(q[cur].shadowKeys, q[cur].counts + 1, bucketHist);
+				k_bucket_scan<<<1, 1024, 0, c->stream>>>(bucketHist, bucketOffsets, bucketRunning);
+				k_bucket_scatter<<<Blocks(ubShadow, perBlock), 256, 0, c->stream>>>(q[cur].shadow, q[cur].shadowKeys, q[cur].counts + 1, bucketOffsets, bucketRunning, c->sortedShadow.p);
+				c->stats.kernel_launches += 3;
 				shadowQueue = c->sortedShadow.p;
-			}
-			if (bucketActive && ubActive > 0) {
-				k_bucket_scan<<<1, 1024, 0, c->stream>>>(q[cur].activeHist, bucketOffsets, bucketRunning);
-				k_bucket_scatter<<<Blocks(ubActive, 256), 256, 0, c->stream>>>(q[cur].active, q[cur].activeKeys, q[cur].counts + 2, bucketOffsets, bucketRunning, c->sortedActive.p);
-				c->stats.kernel_launches += 2;
-				qin.active = c->sortedActive.p;
 			}
 		}
 		// The two traces of a wave are independent (different queues, different result arrays):
@@ -520,9 +514,6 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
-		if (bucketing) CU(cudaMemsetAsync(q[cur ^ 1].hist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
-		if (bucketing) CU(cudaMemsetAsync(q[cur ^ 1].shadowHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
-		if (bucketing && bucketActive) CU(cudaMemsetAsync(q[cur ^ 1].activeHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
 		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
@@ -601,7 +592,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.shadowKeys = nullptr;
 	// evA/evC/evD are reused inside RunWaves when timing; the render bracket has its own pair
 	cudaEvent_t r0, r1;
 	CU(cudaEventCreate(&r0)); CU(cudaEventCreate(&r1));
@@ -658,7 +649,7 @@ int agpt_trace_primary(agpt_ctx* c, int sample, uint32_t flags, agpt_hit* out_ho
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.shadowKeys = nullptr;
 	GenParams g;
 	memset(&g, 0, sizeof(g));
 	g.n = (int)wh; g.first_sample = sample; g.sample_stride = 1;
@@ -680,7 +671,7 @@ int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uin
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.shadowKeys = nullptr;
 	DevBuf<float> rays;
 	DevBuf<uint32_t> seeds;
 	CU(rays.Upload(rays7, 7 * (size_t)n, c->stream));
@@ -704,7 +695,7 @@ static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, 
 	DScene sc = MakeScene(c);
 	PathState ps = MakePathState(c);
 	WaveQueues q0;
-	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.hist = nullptr; q0.shadowKeys = nullptr; q0.shadowHist = nullptr; q0.activeKeys = nullptr; q0.activeHist = nullptr;
+	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.shadowKeys = nullptr;
 	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;

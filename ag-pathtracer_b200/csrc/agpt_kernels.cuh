@@ -71,13 +71,9 @@ struct PathState {
 struct WaveQueues {
 	int* closest;        // entries path*2 + kind (0 = path ray, 1 = MIS ray)
 	unsigned short* keys; // bucket key of each closest-queue entry
-	int* hist;           // AGPT_BUCKETS counters: entries per bucket
+	int* shadow;         // path indices with a shadow ray
 	unsigned short* shadowKeys;
-	int* shadowHist;
-	unsigned short* activeKeys;
-	int* activeHist;
-	int* shadow;         // entries path
-	int* active;         // paths that take part in the next shade
+	int* active;         // path indices shade works on
 	int* counts;         // [0] closest, [1] shadow, [2] active
 };
 
@@ -110,14 +106,43 @@ __device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D) {
 	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
 	return (cell << 3) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
 }
-// Histogram add with one atomic per distinct key per warp.  All 32 lanes must call.
-__device__ __forceinline__ void WarpHistAdd(bool pred, int key, int* hist) {
+// ---- bucket pass between shade and the next trace: counting sort of a ray queue by key ------
+// k_bucket_hist (entries per bucket) -> k_bucket_scan (exclusive offsets, one block) ->
+// k_bucket_scatter.  Neighbouring queue entries come from neighbouring paths and so carry the
+// same few keys: global atomics per warp would all land on the same addresses at the same time
+// and serialise in L2.  Both kernels therefore count in block-private shared-memory bins first
+// (1024 entries per block) and touch each global counter once per block.  The order inside a
+// bucket is free: every path's arithmetic is independent of its queue position.
+#define AGPT_BUCKET_ITEMS 4      // entries per thread of the 256-thread bucket kernels
+
+// rank of this lane among the lanes of its warp with the same key, plus the warp's claim on the
+// block's bin (one shared-memory atomic per distinct key per warp).  All 32 lanes must call.
+__device__ __forceinline__ int BlockBinClaim(bool valid, int key, int* bins) {
 	int lane = threadIdx.x & 31;
-	unsigned m = __match_any_sync(0xffffffffu, pred ? key : (AGPT_BUCKETS + lane));
-	if (pred && lane == __ffs(m) - 1) atomicAdd(hist + key, __popc(m));
+	unsigned m = __match_any_sync(0xffffffffu, valid ? key : (AGPT_BUCKETS + lane));
+	int leader = __ffs(m) - 1;
+	int base = 0;
+	if (valid && lane == leader) base = atomicAdd(bins + key, __popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + __popc(m & ((1u << lane) - 1u));
 }
 
-// Bucket pass between shade and the next trace: exclusive scan of the histogram (one block) ...
+__global__ void __launch_bounds__(256) k_bucket_hist(const unsigned short* __restrict__ keys, const int* __restrict__ countPtr, int* hist) {
+	__shared__ int bins[AGPT_BUCKETS];
+	for (int b = threadIdx.x; b < AGPT_BUCKETS; b += 256) bins[b] = 0;
+	__syncthreads();
+	const int count = *countPtr;
+	const int base = blockIdx.x * 256 * AGPT_BUCKET_ITEMS;
+#pragma unroll
+	for (int k = 0; k < AGPT_BUCKET_ITEMS; k++) {
+		int i = base + k * 256 + threadIdx.x;
+		int key = keys[i];                 // (allocation slack: unconditional)
+		BlockBinClaim(i < count, key, bins);
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < AGPT_BUCKETS; b += 256) { int c = bins[b]; if (c) atomicAdd(hist + b, c); }
+}
+
 __global__ void __launch_bounds__(1024) k_bucket_scan(const int* hist, int* offsets, int* running) {
 	__shared__ int warpSums[32];
 	const int PER = AGPT_BUCKETS / 1024;   // AGPT_BUCKETS is a multiple of 1024 for AGPT_CELL_BITS >= 3
@@ -138,21 +163,29 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const int* hist, int* offs
 	int base = x - sum + (w > 0 ? warpSums[w - 1] : 0);
 	for (int k = 0; k < PER; k++) { offsets[t * PER + k] = base; running[t * PER + k] = 0; base += v[k]; }
 }
-// ... and the scatter of the queue entries into bucket order (order inside a bucket is free:
-// every path's arithmetic is independent of its queue position).
+
 __global__ void __launch_bounds__(256) k_bucket_scatter(const int* __restrict__ in, const unsigned short* __restrict__ keys, const int* __restrict__ countPtr,
 		const int* __restrict__ offsets, int* running, int* __restrict__ out) {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	int entry = in[i], rawKey = keys[i];
-	bool valid = i < *countPtr;
-	int lane = threadIdx.x & 31;
-	int key = valid ? rawKey : (AGPT_BUCKETS + lane);
-	unsigned m = __match_any_sync(0xffffffffu, key);
-	int leader = __ffs(m) - 1;
-	int base = 0;
-	if (valid && lane == leader) base = atomicAdd(running + key, __popc(m));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	if (valid) out[offsets[key] + base + __popc(m & ((1u << lane) - 1u))] = entry;
+	__shared__ int bins[AGPT_BUCKETS];     // entries of this block per bucket, then: where the block's group starts in `out`
+	for (int b = threadIdx.x; b < AGPT_BUCKETS; b += 256) bins[b] = 0;
+	__syncthreads();
+	const int count = *countPtr;
+	const int base = blockIdx.x * 256 * AGPT_BUCKET_ITEMS;
+	int entry[AGPT_BUCKET_ITEMS], key[AGPT_BUCKET_ITEMS], rank[AGPT_BUCKET_ITEMS];
+#pragma unroll
+	for (int k = 0; k < AGPT_BUCKET_ITEMS; k++) {
+		int i = base + k * 256 + threadIdx.x;
+		entry[k] = in[i]; key[k] = keys[i];
+		rank[k] = BlockBinClaim(i < count, key[k], bins);
+	}
+	__syncthreads();
+	for (int b = threadIdx.x; b < AGPT_BUCKETS; b += 256) { int c = bins[b]; if (c) bins[b] = offsets[b] + atomicAdd(running + b, c); }
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < AGPT_BUCKET_ITEMS; k++) {
+		int i = base + k * 256 + threadIdx.x;
+		if (i < count) out[bins[key[k]] + rank[k]] = entry[k];
+	}
 }
 
 // ---- path generation: myapp.cpp:165-167 + Camera::GetRay (camera.h:58-64) ----------------
@@ -737,14 +770,9 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 		}
 		__syncthreads();
 		if (emitExtend) { int slot = queueBase[0] + warpCount[warp][0] + __popc(mE & below); qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
-		WarpHistAdd(emitExtend, keyExtend, qout.hist);
 		if (emitMis) { int slot = queueBase[0] + warpCount[warp][1] + __popc(mM & below); qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
-		WarpHistAdd(emitMis, keyMis, qout.hist);
 		if (emitShadow) { int slot = queueBase[1] + warpCount[warp][2] + __popc(mS & below); qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
-		WarpHistAdd(emitShadow, keyShadow, qout.shadowHist);
-		int keyActive = emitExtend ? keyExtend : 0;      // paths that only wait for their NEE go to bucket 0
-		if (stayActive) { int slot = queueBase[2] + warpCount[warp][3] + __popc(mA & below); qout.active[slot] = path; qout.activeKeys[slot] = (unsigned short)keyActive; }
-		WarpHistAdd(stayActive, keyActive, qout.activeHist);
+		if (stayActive) { int slot = queueBase[2] + warpCount[warp][3] + __popc(mA & below); qout.active[slot] = path; }
 
 		// ray statistics: one atomic per counter per block
 		if (threadIdx.x < 6 && blockStats[threadIdx.x]) {
