@@ -251,6 +251,8 @@ def main():
 
     for k in range(args.warmup):
         step(k)
+    if world > 1:
+        pkg.multigpu.allreduce_accumulator(accum)         # warm-up of the collective too (NCCL sets its channels up on first use)
     accum.zero_()
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
