@@ -96,6 +96,7 @@ struct agpt_ctx {
 	bool asyncWaves = false;      // AGPT_ASYNC_WAVES=1: run one wave ahead of the landed queue counts instead of syncing
 	                              // every wave.  Measured slower (N=1: 133 vs 130.5 ms/step, N=8: 142.8 vs 139.3): the loose
 	                              // launch bounds and the extra empty wave cost more than the ~30 us sync gaps they remove.
+	size_t maxPathsPerBatch = kMaxPathsPerBatch;   // AGPT_BATCH_LOG2 (environment) overrides the compiled-in size
 	bool overlapAny = true;       // AGPT_OVERLAP_ANY=0: any-hit trace on the main stream after the closest-hit trace
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 };
@@ -229,6 +230,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaMallocHost((void**)&c->hostCounts, 8 * 3 * sizeof(int)));
 	for (auto& e : c->ringEvents) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
+	if (const char* e = getenv("AGPT_BATCH_LOG2")) { int b = atoi(e); if (b >= 10 && b <= 28) c->maxPathsPerBatch = (size_t)1 << b; }
 	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	*out = c;
@@ -583,7 +585,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	NEED(c->accum != nullptr, AGPT_ERR_STATE, "no accumulator");
 	CU(cudaSetDevice(c->device));
 	const size_t wh = (size_t)c->width * c->height;
-	int perBatch = (int)(kMaxPathsPerBatch / wh);
+	int perBatch = (int)(c->maxPathsPerBatch / wh);
 	if (perBatch < 1) perBatch = 1;
 	if (perBatch > num_samples) perBatch = num_samples;
 	if (num_samples == 0) return AGPT_OK;

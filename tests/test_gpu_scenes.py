@@ -124,13 +124,14 @@ def test_filtered_slab_test_equals_strict(agpt, gpu_ctx, cfg, level):
 
 
 def test_bucketing_does_not_change_results(agpt):
-    """Queue order is free: with and without the ray-bucket pass the film is bit-identical."""
+    """Queue order and batching are free: without the ray-bucket pass, without the side stream,
+    with the run-ahead wave loop and with one sample per batch the film is bit-identical."""
     import os
     cfg, level, W, H = 3, 3, 160, 90
     d = agpt.config_defaults(cfg)
     hs = agpt.HostScene(cfg, level)
     films = []
-    for env in ({"AGPT_BUCKET_RAYS": "0"}, {"AGPT_BUCKET_RAYS": "1", "AGPT_BUCKET_ACTIVE": "1"}, {"AGPT_ASYNC_WAVES": "1"}):
+    for env in ({"AGPT_BUCKET_RAYS": "0"}, {"AGPT_BUCKET_RAYS": "1", "AGPT_OVERLAP_ANY": "0"}, {"AGPT_ASYNC_WAVES": "1"}, {"AGPT_BATCH_LOG2": "14"}):
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -145,4 +146,5 @@ def test_bucketing_does_not_change_results(agpt):
         ctx.render(0, 4, d["max_depth"], d["depth_arg"])
         films.append(ctx.read_accum())
         ctx.close()
-    assert np.array_equal(bits(films[0]), bits(films[1])) and np.array_equal(bits(films[0]), bits(films[2]))
+    for f in films[1:]:
+        assert np.array_equal(bits(films[0]), bits(f))
