@@ -44,6 +44,14 @@ struct MeshStore {
 	void Free() { nodes.Free(); tris.Free(); normals.Free(); uvs.Free(); ids.Free(); }
 };
 
+#ifndef AGPT_BATCH_LOG2
+#define AGPT_BATCH_LOG2 25
+#endif
+// Paths in flight per batch.  2^25 = 33.5 M slots ~ 8.5 GB of wavefront state + queues (sized for 180 GB of
+// HBM3e).  Bigger batches mean fuller waves and more rays per bucket, i.e. more coherent warps: cfg 3 at
+// 16 spp runs in 106 / 98 / 94 ms with 2^23 / 2^24 / 2^25 slots.
+static const size_t kMaxPathsPerBatch = (size_t)1 << AGPT_BATCH_LOG2;
+
 struct agpt_ctx {
 	int device = 0;
 	cudaStream_t ownStream = nullptr, stream = nullptr;
@@ -100,14 +108,6 @@ struct agpt_ctx {
 	bool overlapAny = true;       // AGPT_OVERLAP_ANY=0: any-hit trace on the main stream after the closest-hit trace
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 };
-
-#ifndef AGPT_BATCH_LOG2
-#define AGPT_BATCH_LOG2 25
-#endif
-// Paths in flight per batch.  2^25 = 33.5 M slots ~ 8.5 GB of wavefront state + queues (sized for 180 GB of
-// HBM3e).  Bigger batches mean fuller waves and more rays per bucket, i.e. more coherent warps: cfg 3 at
-// 16 spp runs in 106 / 98 / 94 ms with 2^23 / 2^24 / 2^25 slots.
-static const size_t kMaxPathsPerBatch = (size_t)1 << AGPT_BATCH_LOG2;
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
