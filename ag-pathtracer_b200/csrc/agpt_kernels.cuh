@@ -6,7 +6,8 @@
 // of the PREVIOUS vertex into L (its shadow / MIS rays have just been traced), then handles
 // the new hit: emission, termination, null-material skip-through, light sampling
 // (UniformSampleOneLight + EstimateDirect, integrator.h:38-105), BSDF sampling, Russian
-// roulette, and queues the rays of the next wave with warp-ballot compaction.
+// roulette, and queues the rays of the next wave (warp ballots + a shared-memory prefix over the
+// block's warps: one atomic per queue per block).
 // The per-path RNG state lives in HBM, so the draw order inside a path is the reference's
 // whatever the scheduling.
 #pragma once
@@ -80,17 +81,6 @@ struct WaveQueues {
 struct RayCounters {     // device-side totals, see agpt_stats
 	unsigned long long rays_closest, rays_shadow, rays_mis, rays_skip, rays_mis_culled, rays_tail_culled;
 };
-
-// ---- warp-aggregated append (warp-ballot ray-queue compaction) ---------------------------
-// All 32 lanes must call.  Returns the slot for lanes with pred, one atomic per warp.
-__device__ __forceinline__ int WarpAppend(bool pred, int* counter) {
-	unsigned mask = __ballot_sync(0xffffffffu, pred);
-	int lane = threadIdx.x & 31;
-	int base = 0;
-	if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	return base + __popc(mask & ((1u << lane) - 1u));
-}
 
 // Ray bucket: rays that leave the same primitive in the same direction octant walk similar parts
 // of the trees in the same near/far order, so putting them next to each other in the queue
