@@ -212,7 +212,26 @@ struct GenParams {
 	const int* ss;
 	const float* rays7;    // optional explicit rays (li_rays); O, D, tmax
 	const uint32_t* seeds;
+	int tiled;             // whole-film mode: path slots in 8x4-pixel tiles (agpt_render) instead of rows
 };
+
+// Path slot <-> pixel.  Rendering lays the path slots of a sample out in 8x4-pixel tiles, so a
+// warp's 32 camera rays cover a compact patch of the film instead of a 32x1 strip: they walk the
+// same nodes and mostly shade the same material.  (Every draw of a path depends on its pixel and
+// sample index only, never on its slot.)  Films whose size is not a multiple of the tile, and
+// the hit-table entry points, use the row-major order.
+__device__ __forceinline__ void SlotToPixel(int slot, int width, int height, bool tiled, int& x, int& y) {
+	if (tiled && (width & 7) == 0 && (height & 3) == 0) {
+		int tile = slot >> 5, within = slot & 31, tilesX = width >> 3;
+		x = (tile % tilesX) * 8 + (within & 7);
+		y = (tile / tilesX) * 4 + (within >> 3);
+	}
+	else { x = slot % width; y = slot / width; }
+}
+__device__ __forceinline__ int PixelToSlot(int x, int y, int width, int height, bool tiled) {
+	if (tiled && (width & 7) == 0 && (height & 3) == 0) return ((y >> 2) * (width >> 3) + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7);
+	return y * width + x;
+}
 
 __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQueues q, GenParams g) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,8 +249,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 		if (g.xs) { x = g.xs[i]; y = g.ys[i]; sample = g.ss[i]; }
 		else {
 			int wh = sc.width * sc.height;
-			int pixel = i % wh;
-			x = pixel % sc.width; y = pixel / sc.width;
+			SlotToPixel(i % wh, sc.width, sc.height, g.tiled != 0, x, y);
 			sample = g.first_sample + (i / wh) * g.sample_stride;
 		}
 		rng = StreamSeed((uint32_t)(y * sc.width + x), (uint32_t)sample);
@@ -781,10 +799,11 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ L
 	int wh = width * height;
 	if (pixel >= wh) return;
 	int x = pixel % width, y = pixel / width;
+	const int slot = PixelToSlot(x, y, width, height, true);       // agpt_render generates tiled
 	float4* dst = accum + (size_t)(height - 1 - y) * width + x;
 	float4 a = *dst;
 	for (int s = 0; s < samplesInBatch; s++) {
-		float4 c = Lout[(size_t)s * wh + pixel];
+		float4 c = Lout[(size_t)s * wh + slot];
 		float lum = 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z;     // Luminance (precomp.h:717)
 		if (isnan(c.x) || isnan(c.y) || isnan(c.z) || isinf(lum)) c = make_float4(0.f, 0.f, 0.f, 0.f);
 		a.x += c.x; a.y += c.y; a.z += c.z;
