@@ -604,7 +604,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 		int n = (int)(wh * ns);
 		GenParams g;
 		memset(&g, 0, sizeof(g));
-		g.n = n; g.first_sample = first_sample + done * sample_stride; g.sample_stride = sample_stride; g.tiled = 1;
+		g.n = n; g.first_sample = first_sample + done * sample_stride; g.sample_stride = sample_stride; g.tiled = 1; g.samples = ns;
 		k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
 		CU(cudaGetLastError());
 		c->stats.kernel_launches++;

@@ -212,12 +212,14 @@ struct GenParams {
 	const int* ss;
 	const float* rays7;    // optional explicit rays (li_rays); O, D, tmax
 	const uint32_t* seeds;
-	int tiled;             // whole-film mode: path slots in 8x4-pixel tiles (agpt_render) instead of rows
+	int tiled;             // whole-film mode of agpt_render: slot = tile-order pixel slot * samples + sample (else sample-major rows)
+	int samples;           // samples per pixel in this batch (tiled mode)
 };
 
-// Path slot <-> pixel.  Rendering lays the path slots of a sample out in 8x4-pixel tiles, so a
-// warp's 32 camera rays cover a compact patch of the film instead of a 32x1 strip: they walk the
-// same nodes and mostly shade the same material.  (Every draw of a path depends on its pixel and
+// Path slot <-> pixel.  Rendering keeps the samples of a pixel in neighbouring slots and orders
+// the pixels in 8x4 tiles, so a warp's 32 camera rays cover a compact patch of the film (at 16
+// samples per batch: two pixels) instead of a 32x1 strip of one sample: they walk the same nodes
+// and mostly shade the same material.  (Every draw of a path depends on its pixel and
 // sample index only, never on its slot.)  Films whose size is not a multiple of the tile, and
 // the hit-table entry points, use the row-major order.
 __device__ __forceinline__ void SlotToPixel(int slot, int width, int height, bool tiled, int& x, int& y) {
@@ -249,8 +251,15 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 		if (g.xs) { x = g.xs[i]; y = g.ys[i]; sample = g.ss[i]; }
 		else {
 			int wh = sc.width * sc.height;
-			SlotToPixel(i % wh, sc.width, sc.height, g.tiled != 0, x, y);
-			sample = g.first_sample + (i / wh) * g.sample_stride;
+			if (g.tiled) {
+				// samples of a pixel sit next to each other, pixels in 8x4 tiles
+				SlotToPixel(i / g.samples, sc.width, sc.height, true, x, y);
+				sample = g.first_sample + (i % g.samples) * g.sample_stride;
+			}
+			else {
+				SlotToPixel(i % wh, sc.width, sc.height, false, x, y);
+				sample = g.first_sample + (i / wh) * g.sample_stride;
+			}
 		}
 		rng = StreamSeed((uint32_t)(y * sc.width + x), (uint32_t)sample);
 		ray = CameraRay(sc, x, y, rng);
@@ -799,11 +808,11 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ L
 	int wh = width * height;
 	if (pixel >= wh) return;
 	int x = pixel % width, y = pixel / width;
-	const int slot = PixelToSlot(x, y, width, height, true);       // agpt_render generates tiled
+	const size_t slot = (size_t)PixelToSlot(x, y, width, height, true) * samplesInBatch;       // agpt_render generates tiled
 	float4* dst = accum + (size_t)(height - 1 - y) * width + x;
 	float4 a = *dst;
 	for (int s = 0; s < samplesInBatch; s++) {
-		float4 c = Lout[(size_t)s * wh + slot];
+		float4 c = Lout[slot + s];
 		float lum = 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z;     // Luminance (precomp.h:717)
 		if (isnan(c.x) || isnan(c.y) || isnan(c.z) || isinf(lum)) c = make_float4(0.f, 0.f, 0.f, 0.f);
 		a.x += c.x; a.y += c.y; a.z += c.z;
