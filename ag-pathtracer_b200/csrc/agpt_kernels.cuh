@@ -67,7 +67,7 @@ struct PathState {
 #ifndef AGPT_CELL_BITS
 #define AGPT_CELL_BITS 3
 #endif
-#define AGPT_BUCKETS (8 << (3 * AGPT_CELL_BITS))   // ray buckets: 3 bits direction octant | 3 x AGPT_CELL_BITS bits grid cell of the ray origin
+#define AGPT_BUCKETS (16 << (3 * AGPT_CELL_BITS))  // ray buckets: 4 bits direction code | 3 x AGPT_CELL_BITS bits grid cell of the ray origin
 
 struct WaveQueues {
 	int* closest;        // entries path*2 + kind (0 = path ray, 1 = MIS ray)
@@ -85,7 +85,9 @@ struct RayCounters {     // device-side totals, see agpt_stats
 // Ray bucket: rays that leave the same primitive in the same direction octant walk similar parts
 // of the trees in the same near/far order, so putting them next to each other in the queue
 // raises both the SIMT efficiency of the lockstep walk and the L1/L2 hit rate.
-__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D) {
+// Direction code: the octant (0..7), or for a shadow ray aimed at an area light 8 + (light & 7) --
+// rays from one cell to one small light are as alike as rays get.
+__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, int areaLight = -1) {
 	const int hi = (1 << AGPT_CELL_BITS) - 1;
 	int cx = min(max((int)((O.x - sc.cellLo[0]) * sc.cellScale[0]), 0), hi);
 	int cy = min(max((int)((O.y - sc.cellLo[1]) * sc.cellScale[1]), 0), hi);
@@ -94,7 +96,8 @@ __device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D) {
 	int cell = 0;
 #pragma unroll
 	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
-	return (cell << 3) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
+	if (areaLight >= 0) return (cell << 4) | 8 | (areaLight & 7);
+	return (cell << 4) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
 }
 // ---- bucket pass between shade and the next trace: counting sort of a ray queue by key ------
 // k_bucket_hist (entries per bucket) -> k_bucket_scan (exclusive offsets, one block) ->
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 						ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
 						ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
 						emitShadow = true;
-						keyShadow = RayBucket(sc, vis.O, vis.D);
+						keyShadow = RayBucket(sc, vis.O, vis.D, lightType == AGPT_LIGHT_AREA ? numLight : -1);
 					}
 				}
 				if (smp[0].ok) {
