@@ -64,6 +64,9 @@ struct PathState {
 	StateArray<float4> Lout;        // finished radiance per path slot
 };
 
+#ifndef AGPT_STEEP_BIT
+#define AGPT_STEEP_BIT 1
+#endif
 #ifndef AGPT_CELL_BITS
 #define AGPT_CELL_BITS 3
 #endif
@@ -87,7 +90,7 @@ struct RayCounters {     // device-side totals, see agpt_stats
 // raises both the SIMT efficiency of the lockstep walk and the L1/L2 hit rate.
 // Direction code: the octant (0..7), or for a shadow ray aimed at an area light 8 + (light & 7) --
 // rays from one cell to one small light are as alike as rays get.
-__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, int areaLight = -1) {
+__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, int areaLight = -1, bool steep = false) {
 	const int hi = (1 << AGPT_CELL_BITS) - 1;
 	int cx = min(max((int)((O.x - sc.cellLo[0]) * sc.cellScale[0]), 0), hi);
 	int cy = min(max((int)((O.y - sc.cellLo[1]) * sc.cellScale[1]), 0), hi);
@@ -97,7 +100,9 @@ __device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, i
 #pragma unroll
 	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
 	if (areaLight >= 0) return (cell << 4) | 8 | (areaLight & 7);
-	return (cell << 4) | (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
+	int code = (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
+	if (AGPT_STEEP_BIT && steep && fabsf(D.y) > fmaxf(fabsf(D.x), fabsf(D.z))) code |= 8;   // closest-hit queue: mostly-vertical rays apart
+	return (cell << 4) | code;
 }
 // ---- bucket pass between shade and the next trace: counting sort of a ray queue by key ------
 // k_bucket_hist (entries per bucket) -> k_bucket_scan (exclusive offsets, one block) ->
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 				ps.rayO[path] = make_float4(nr.O.x, nr.O.y, nr.O.z, nr.t);
 				ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 				emitExtend = true; skipRay = true; stayActive = true;
-				keyExtend = RayBucket(sc, nr.O, nr.D);
+				keyExtend = RayBucket(sc, nr.O, nr.D, -1, true);
 			}
 			else { full = true; mat = sc.mats + prim.material; }
 		}
@@ -698,7 +703,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 							ps.misD[path] = make_float4(mr.D.x, mr.D.y, mr.D.z, 0.f);
 							if (canReachLight) {
 								emitMis = true;
-								keyMis = RayBucket(sc, mr.O, mr.D);
+								keyMis = RayBucket(sc, mr.O, mr.D, -1, true);
 							}
 						}
 					}
@@ -735,7 +740,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, Pa
 				ps.rayD[path] = make_float4(nr.D.x, nr.D.y, nr.D.z, 0.f);
 				ps.beta[path] = make_float4(beta.x, beta.y, beta.z, 0.f);
 				emitExtend = true; stayActive = true;
-				keyExtend = RayBucket(sc, nr.O, nr.D);
+				keyExtend = RayBucket(sc, nr.O, nr.D, -1, true);
 			}
 			else if (emitShadow || emitMis) { flags |= PF_NO_CONTINUE; stayActive = true; }
 			else finished = true;
