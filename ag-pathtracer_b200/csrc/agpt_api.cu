@@ -77,6 +77,9 @@ struct agpt_ctx {
 	agpt_camera cam;
 	bool haveCam = false;
 	float boundsLo[3] = { -1, -1, -1 }, boundsHi[3] = { 1, 1, 1 };   // bounded geometry (mesh roots), for ray bucketing only
+	float gridLo[3] = { -1, -1, -1 }, gridHi[3] = { 1, 1, 1 };       // ... refined from where the camera's rays actually land (CalibrateBucketGrid)
+	bool gridCalibrated = false;
+	bool calibrateGrid = true;    // AGPT_BUCKET_CALIBRATE=0: keep the grid on the mesh bounds
 	int width = 0, height = 0;
 
 	// film
@@ -109,6 +112,10 @@ struct agpt_ctx {
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 };
 
+static void SetBucketGrid(DScene& s, const float* lo, const float* hi) {
+	for (int a = 0; a < 3; a++) { s.cellLo[a] = lo[a]; float e = hi[a] - lo[a]; s.cellScale[a] = e > 0 ? (float)(1 << AGPT_CELL_BITS) / e : 0.f; }
+}
+
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
 	s.prims = c->prims.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
@@ -116,7 +123,7 @@ static DScene MakeScene(const agpt_ctx* c) {
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
 	s.envRgb = c->envRgb.p; s.envFunc = c->envFunc.p; s.envCdf = c->envCdf.p; s.envFuncInt = c->envFuncInt; s.envW = c->envW; s.envH = c->envH;
 	s.width = c->width; s.height = c->height;
-	for (int a = 0; a < 3; a++) { s.cellLo[a] = c->boundsLo[a]; float e = c->boundsHi[a] - c->boundsLo[a]; s.cellScale[a] = e > 0 ? (float)(1 << AGPT_CELL_BITS) / e : 0.f; }
+	SetBucketGrid(s, c->gridCalibrated ? c->gridLo : c->boundsLo, c->gridCalibrated ? c->gridHi : c->boundsHi);
 	s.cam = c->cam;
 	return s;
 }
@@ -231,6 +238,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	for (auto& e : c->ringEvents) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BATCH_LOG2")) { int b = atoi(e); if (b >= 10 && b <= 28) c->maxPathsPerBatch = (size_t)1 << b; }
+	if (const char* e = getenv("AGPT_BUCKET_CALIBRATE")) c->calibrateGrid = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	*out = c;
@@ -276,6 +284,7 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	NEED(c != nullptr && n >= 0 && (n == 0 || meshes != nullptr), AGPT_ERR_INVALID, "bad mesh table");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
+	c->gridCalibrated = false;
 	for (auto& m : c->meshStore) m.Free();
 	c->meshStore.assign(n, MeshStore());
 	std::vector<DMesh> table(n);
@@ -358,6 +367,7 @@ int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
 	NEED(c != nullptr && cam != nullptr, AGPT_ERR_INVALID, "null camera");
 	c->cam = *cam;
 	c->haveCam = true;
+	c->gridCalibrated = false;
 	return AGPT_OK;
 }
 
@@ -448,8 +458,45 @@ int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
 // empty waves launched past the end are no-ops.  AGPT_FLAG_TIMING brackets the kernel classes
 // of every wave with events.
 static const int kMaxAhead = 2, kRing = 8;
-static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max_depth, int rr_depth_arg, uint32_t flags) {
+// The bucket grid should resolve the part of the scene the rays are in, not the scene's bounding
+// box (cfg 3: a 40-unit backdrop around 15 units of objects left 12 of the 512 cells in use).
+// Once per scene and camera, after the first camera rays have been traced, a strided sample of
+// their hit points is read back and the grid is laid over mean +- 2.5 sigma of it.  Ray order
+// only: results do not depend on the grid.
+static int CalibrateBucketGrid(agpt_ctx* c, const PathState& ps, int n) {
+	const int samples = n < 65536 ? n : 65536;
+	const size_t pitch = (size_t)(n / samples) * sizeof(float4);
+	std::vector<float4> o(samples), d(samples), h(samples);
+	CU(cudaMemcpy2DAsync(o.data(), sizeof(float4), (const float4*)ps.rayO, pitch, sizeof(float4), samples, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpy2DAsync(d.data(), sizeof(float4), (const float4*)ps.rayD, pitch, sizeof(float4), samples, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpy2DAsync(h.data(), sizeof(float4), (const float4*)ps.hitA, pitch, sizeof(float4), samples, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	double sum[3] = { 0, 0, 0 }, sq[3] = { 0, 0, 0 };
+	long hits = 0;
+	for (int i = 0; i < samples; i++) {
+		int prim; memcpy(&prim, &h[i].w, sizeof(prim));
+		float t = h[i].x;
+		if (prim < 0 || !(t > 0.f) || !(t < 1e30f)) continue;
+		double p[3] = { o[i].x + (double)t * d[i].x, o[i].y + (double)t * d[i].y, o[i].z + (double)t * d[i].z };
+		for (int a = 0; a < 3; a++) { sum[a] += p[a]; sq[a] += p[a] * p[a]; }
+		hits++;
+	}
+	c->gridCalibrated = true;
+	for (int a = 0; a < 3; a++) { c->gridLo[a] = c->boundsLo[a]; c->gridHi[a] = c->boundsHi[a]; }
+	if (hits < 256) return AGPT_OK;                       // too little to go by: keep the mesh bounds
+	for (int a = 0; a < 3; a++) {
+		double mean = sum[a] / hits, var = sq[a] / hits - mean * mean;
+		double sigma = var > 0 ? sqrt(var) : 0;
+		if (sigma <= 0) continue;
+		c->gridLo[a] = (float)(mean - 2.5 * sigma);
+		c->gridHi[a] = (float)(mean + 2.5 * sigma);
+	}
+	return AGPT_OK;
+}
+
+static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int max_depth, int rr_depth_arg, uint32_t flags) {
 	const bool count = flags & AGPT_FLAG_COUNTERS, timing = flags & AGPT_FLAG_TIMING, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
+	DScene sc = scIn;
 	WaveQueues q[2];
 	for (int k = 0; k < 2; k++) {
 		q[k].closest = c->queues[0 + k].p; q[k].shadow = c->queues[2 + k].p; q[k].active = c->queues[4 + k].p;
@@ -503,6 +550,12 @@ static int RunWaves(agpt_ctx* c, const DScene& sc, PathState& ps, int n, int max
 		if (ubClosest > 0) {
 			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest);
 			c->stats.kernel_launches++; c->stats.launches_closest++;
+		}
+		if (wave == 0 && bucketing && !c->gridCalibrated && c->calibrateGrid && n >= 4096) {
+			// first camera rays of this scene and camera: lay the bucket grid where they land
+			int rcode = CalibrateBucketGrid(c, ps, n);
+			if (rcode != AGPT_OK) return rcode;
+			SetBucketGrid(sc, c->gridLo, c->gridHi);
 		}
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (fork) {
