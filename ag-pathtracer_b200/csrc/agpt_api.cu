@@ -458,6 +458,7 @@ int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
 // empty waves launched past the end are no-ops.  AGPT_FLAG_TIMING brackets the kernel classes
 // of every wave with events.
 static const int kMaxAhead = 2, kRing = 8;
+static const int kSmallWave = 16384;
 // The bucket grid should resolve the part of the scene the rays are in, not the scene's bounding
 // box (cfg 3: a 40-unit backdrop around 15 units of objects left 12 of the 512 cells in use).
 // Once per scene and camera, after the first camera rays have been traced, a strided sample of
@@ -523,8 +524,9 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		WaveQueues qin = q[cur];
 		if (wave > 0 && bucketing) {
 			// bucket pass: rays that start in the same cell going the same way end up adjacent
+			// (not worth its six launches for the last few thousand rays of a batch)
 			const int perBlock = 256 * AGPT_BUCKET_ITEMS;
-			if (ubClosest > 0) {
+			if (ubClosest >= kSmallWave) {
 				CU(cudaMemsetAsync(bucketHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 				k_bucket_hist<<<Blocks(ubClosest, perBlock), 256, 0, c->stream>>>(q[cur].keys, q[cur].counts + 0, bucketHist);
 				k_bucket_scan<<<1, 1024, 0, c->stream>>>(bucketHist, bucketOffsets, bucketRunning);
@@ -532,7 +534,7 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 				c->stats.kernel_launches += 3;
 				closestQueue = c->sortedClosest.p;
 			}
-			if (ubShadow > 0) {
+			if (ubShadow >= kSmallWave) {
 				CU(cudaMemsetAsync(bucketHist, 0, AGPT_BUCKETS * sizeof(int), c->stream));
 				k_bucket_hist<<<Blocks(ubShadow, perBlock), 256, 0, c->stream>>>(q[cur].shadowKeys, q[cur].counts + 1, bucketHist);
 				k_bucket_scan<<<1, 1024, 0, c->stream>>>(bucketHist, bucketOffsets, bucketRunning);
@@ -603,7 +605,10 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		// ---- consume the copies that have landed (block only when too far ahead, or when timing) ----
 		while (ringTail < ringHead) {
 			int s = ringTail % kRing;
-			bool mustWait = timing || !c->asyncWaves || (ringHead - ringTail) >= kMaxAhead;
+			// small waves (the stragglers at the end of a batch) are launched from the last known
+			// bounds without waiting for their counts: nothing to lose on a few thousand entries
+			bool runAhead = c->asyncWaves || ubActive < kSmallWave;
+			bool mustWait = timing || !runAhead || (ringHead - ringTail) >= kMaxAhead;
 			cudaError_t e = mustWait ? cudaEventSynchronize(c->ringEvents[s]) : cudaEventQuery(c->ringEvents[s]);
 			if (e == cudaErrorNotReady) break;
 			if (e != cudaSuccess) return Fail(AGPT_ERR_CUDA, std::string("wave loop: ") + cudaGetErrorString(e));
