@@ -66,6 +66,7 @@ struct agpt_ctx {
 	DevBuf<agpt_sphere> spheres;
 	DevBuf<agpt_plane> planes;
 	DevBuf<agpt_prim> prims;
+	DevBuf<int> sphereRun;
 	DevBuf<agpt_material> mats;
 	DevBuf<agpt_light> lights;
 	DevBuf<float> envRgb, envFunc, envCdf;
@@ -118,7 +119,7 @@ static void SetBucketGrid(DScene& s, const float* lo, const float* hi) {
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
-	s.prims = c->prims.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
+	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
 	s.envRgb = c->envRgb.p; s.envFunc = c->envFunc.p; s.envCdf = c->envCdf.p; s.envFuncInt = c->envFuncInt; s.envW = c->envW; s.envH = c->envH;
@@ -250,7 +251,7 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	for (auto& m : c->meshStore) m.Free();
-	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->mats.Free(); c->lights.Free();
+	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free();
 	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
@@ -344,7 +345,24 @@ SIMPLE_UPLOAD(agpt_upload_spheres, agpt_sphere, spheres, c->nSpheres = n)
 SIMPLE_UPLOAD(agpt_upload_planes, agpt_plane, planes, c->nPlanes = n)
 SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n)
 SIMPLE_UPLOAD(agpt_upload_lights, agpt_light, lights, c->hostLights.assign(rows, rows + n))
-SIMPLE_UPLOAD(agpt_upload_primitives, agpt_prim, prims, c->hostPrims.assign(rows, rows + n))
+int agpt_upload_primitives(agpt_ctx* c, const agpt_prim* rows, int n) {
+	NEED(c != nullptr && n >= 0 && (n == 0 || rows != nullptr), AGPT_ERR_INVALID, "bad table");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	CU(c->prims.Upload(rows, (size_t)n, c->stream));
+	c->hostPrims.assign(rows, rows + n);
+	// runs of sphere primitives whose payloads are consecutive: the trace kernels walk such a run
+	// straight through the sphere table instead of one primitive record at a time
+	std::vector<int> run((size_t)n, 0);
+	for (int p = n - 1; p >= 0; p--) {
+		if (rows[p].type != AGPT_PRIM_SPHERE) continue;
+		bool chained = p + 1 < n && rows[p + 1].type == AGPT_PRIM_SPHERE && rows[p + 1].payload == rows[p].payload + 1;
+		run[p] = chained ? run[p + 1] + 1 : 1;
+	}
+	CU(c->sphereRun.Upload(run.data(), (size_t)n, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return AGPT_OK;
+}
 
 int agpt_upload_envmap(agpt_ctx* c, const agpt_envmap* env) {
 	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");

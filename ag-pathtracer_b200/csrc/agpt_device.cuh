@@ -32,6 +32,7 @@ struct DMesh {
 
 struct DScene {
 	const agpt_prim* prims;
+	const int* sphereRun;            // per primitive: length of the run of sphere primitives with consecutive payloads starting here (0: not a sphere)
 	const agpt_sphere* spheres;
 	const agpt_plane* planes;
 	const DMesh* meshes;

@@ -281,13 +281,19 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 		bool test = lane && !(ANY && found);
 		if (ANY && !__any_sync(0xffffffffu, test)) break;     // warp-uniform early out of IntersectP
 		if (prim.type == AGPT_PRIM_SPHERE) {
-			if (COUNT && test) cnt.analytic_tests++;
-			float t;
-			if (test && SphereTest(sc.spheres[prim.payload], O, D, rayT, t)) {
-				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
-				found = true;
+			// a run of spheres with consecutive payloads: straight through the sphere table
+			const int len = sc.sphereRun[p];
+			const agpt_sphere* sp = sc.spheres + prim.payload;
+			for (int j = 0; j < len; j++) {
+				bool tj = test && !(ANY && found);
+				if (COUNT && tj) cnt.analytic_tests++;
+				float t;
+				if (tj && SphereTest(sp[j], O, D, rayT, t)) {
+					if (!ANY) { rayT = t; hit.t = t; hit.prim = p + j; hit.slot = -1; }
+					found = true;
+				}
 			}
-			p++;
+			p += len;
 		}
 		else if (prim.type == AGPT_PRIM_PLANE) {
 			if (COUNT && test) cnt.analytic_tests++;
