@@ -67,6 +67,9 @@ struct agpt_ctx {
 	DevBuf<agpt_plane> planes;
 	DevBuf<agpt_prim> prims;
 	DevBuf<int> sphereRun;
+	DevBuf<float4> sphereRunBox;
+	std::vector<agpt_sphere> hostSpheres;
+	bool runsDirty = true;
 	DevBuf<agpt_material> mats;
 	DevBuf<agpt_light> lights;
 	DevBuf<float> envRgb, envFunc, envCdf;
@@ -113,13 +116,54 @@ struct agpt_ctx {
 	bool bucketRays = true;       // bucket pass on the ray queues (AGPT_BUCKET_RAYS=0 turns it off)
 };
 
+// Runs of sphere primitives whose payloads are consecutive: the trace kernels walk such a run
+// straight through the sphere table, and skip it when no ray of the warp can reach its box.
+static int BuildSphereRuns(agpt_ctx* c) {
+	const int n = (int)c->hostPrims.size();
+	std::vector<int> run((size_t)n, 0);
+	std::vector<float4> box(3 * (size_t)n, make_float4(0.f, 0.f, 0.f, 0.f));
+	const std::vector<agpt_prim>& rows = c->hostPrims;
+	for (int p = n - 1; p >= 0; p--) {
+		if (rows[p].type != AGPT_PRIM_SPHERE) continue;
+		bool chained = p + 1 < n && rows[p + 1].type == AGPT_PRIM_SPHERE && rows[p + 1].payload == rows[p].payload + 1;
+		run[p] = chained ? run[p + 1] + 1 : 1;
+	}
+	for (int p = 0; p < n; p++) {
+		if (run[p] == 0) continue;
+		float lo[3] = { 1e30f, 1e30f, 1e30f }, hi[3] = { -1e30f, -1e30f, -1e30f }, rmin = 1e30f;
+		bool ok = true;
+		for (int j = 0; j < run[p]; j++) {
+			int k = rows[p + j].payload;
+			if (k < 0 || k >= (int)c->hostSpheres.size()) { ok = false; break; }
+			const agpt_sphere& sp = c->hostSpheres[k];
+			if (!(sp.r > 0.f)) { ok = false; break; }
+			for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], sp.center[a] - sp.r); hi[a] = fmaxf(hi[a], sp.center[a] + sp.r); }
+			rmin = fminf(rmin, sp.r);
+		}
+		float4* b = &box[3 * (size_t)p];
+		if (!ok) { b[2] = make_float4(0.f, 0.f, 0.f, -1.f); continue; }      // never cull
+		const float grow = 0.05f * rmin;
+		float ctr[3], diag2 = 0.f;
+		for (int a = 0; a < 3; a++) { lo[a] -= grow; hi[a] += grow; ctr[a] = 0.5f * (lo[a] + hi[a]); float h = 0.5f * (hi[a] - lo[a]); diag2 += h * h; }
+		// |O - C_sphere|^2 <= 2 (|O - ctr|^2 + diag2) must stay below 1e5 rmin^2
+		b[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+		b[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+		b[2] = make_float4(ctr[0], ctr[1], ctr[2], 0.5e5f * rmin * rmin - diag2);
+	}
+	CU(c->sphereRun.Upload(run.data(), (size_t)n, c->stream));
+	CU(c->sphereRunBox.Upload(box.data(), box.size(), c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->runsDirty = false;
+	return AGPT_OK;
+}
+
 static void SetBucketGrid(DScene& s, const float* lo, const float* hi) {
 	for (int a = 0; a < 3; a++) { s.cellLo[a] = lo[a]; float e = hi[a] - lo[a]; s.cellScale[a] = e > 0 ? (float)(1 << AGPT_CELL_BITS) / e : 0.f; }
 }
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
-	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
+	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.sphereRunBox = c->sphereRunBox.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
 	s.envRgb = c->envRgb.p; s.envFunc = c->envFunc.p; s.envCdf = c->envCdf.p; s.envFuncInt = c->envFuncInt; s.envW = c->envW; s.envH = c->envH;
@@ -154,6 +198,8 @@ static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	return AGPT_OK;
 }
 
+static int BuildSphereRuns(agpt_ctx* c);
+
 static int CheckReady(agpt_ctx* c, bool needFilm) {
 	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
 	NEED(c->prims.n > 0, AGPT_ERR_STATE, "no primitives uploaded (agpt_upload_primitives)");
@@ -173,6 +219,11 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 		NEED(l.type != AGPT_LIGHT_INFINITE_AREA || c->envW > 0, AGPT_ERR_STATE, "InfiniteAreaLight without an environment map (agpt_upload_envmap)");
 	for (auto& l : c->hostLights)
 		NEED(l.type != AGPT_LIGHT_AREA || (l.prim >= 0 && l.prim < (int)c->hostPrims.size()), AGPT_ERR_INVALID, "area light without a primitive");
+	if (c->runsDirty) {
+		CU(cudaSetDevice(c->device));
+		int rcode = BuildSphereRuns(c);
+		if (rcode != AGPT_OK) return rcode;
+	}
 	return AGPT_OK;
 }
 
@@ -251,7 +302,7 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	for (auto& m : c->meshStore) m.Free();
-	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->mats.Free(); c->lights.Free();
+	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free();
 	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
@@ -341,7 +392,7 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 		counter; \
 		return AGPT_OK; \
 	}
-SIMPLE_UPLOAD(agpt_upload_spheres, agpt_sphere, spheres, c->nSpheres = n)
+SIMPLE_UPLOAD(agpt_upload_spheres, agpt_sphere, spheres, c->nSpheres = n; c->hostSpheres.assign(rows, rows + n); c->runsDirty = true)
 SIMPLE_UPLOAD(agpt_upload_planes, agpt_plane, planes, c->nPlanes = n)
 SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n)
 SIMPLE_UPLOAD(agpt_upload_lights, agpt_light, lights, c->hostLights.assign(rows, rows + n))
@@ -351,15 +402,7 @@ int agpt_upload_primitives(agpt_ctx* c, const agpt_prim* rows, int n) {
 	CU(cudaStreamSynchronize(c->stream));
 	CU(c->prims.Upload(rows, (size_t)n, c->stream));
 	c->hostPrims.assign(rows, rows + n);
-	// runs of sphere primitives whose payloads are consecutive: the trace kernels walk such a run
-	// straight through the sphere table instead of one primitive record at a time
-	std::vector<int> run((size_t)n, 0);
-	for (int p = n - 1; p >= 0; p--) {
-		if (rows[p].type != AGPT_PRIM_SPHERE) continue;
-		bool chained = p + 1 < n && rows[p + 1].type == AGPT_PRIM_SPHERE && rows[p + 1].payload == rows[p].payload + 1;
-		run[p] = chained ? run[p + 1] + 1 : 1;
-	}
-	CU(c->sphereRun.Upload(run.data(), (size_t)n, c->stream));
+	c->runsDirty = true;
 	CU(cudaStreamSynchronize(c->stream));
 	return AGPT_OK;
 }

@@ -33,6 +33,7 @@ struct DMesh {
 struct DScene {
 	const agpt_prim* prims;
 	const int* sphereRun;            // per primitive: length of the run of sphere primitives with consecutive payloads starting here (0: not a sphere)
+	const float4* sphereRunBox;      // per primitive, 3 x float4 for run starts: grown box min.xyz,max.x | max.yz,-,- | centre.xyz, max |O-centre|^2 for the cull to be safe
 	const agpt_sphere* spheres;
 	const agpt_plane* planes;
 	const DMesh* meshes;

@@ -97,6 +97,9 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 #ifndef AGPT_ANY_NEAR_FIRST
 #define AGPT_ANY_NEAR_FIRST 1
 #endif
+#ifndef AGPT_RUN_CULL_MIN
+#define AGPT_RUN_CULL_MIN 4        // sphere runs at least this long get a bounding-box pre-test
+#endif
 #ifndef AGPT_PREFETCH_TRI
 #define AGPT_PREFETCH_TRI 0      // prefetch the triangle of a single-triangle leaf as soon as the walk decides to visit it next
 #endif
@@ -121,14 +124,10 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 // each (a typical ray hits 1-2 of 5 roots).
 // `lane` is false for threads without a ray; they must still call (full-mask votes).
 template <bool ANY, bool COUNT, bool FAST>
-__device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, float3 O, float3 D, float& rayT, HitRecord& hit,
+__device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, float3 O, float3 D, float3 rD, bool filterOk, float& rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	bool found = false;
 	unsigned local[AGPT_STACK_LOCAL];
-	// exact-filtered slab test (agpt_device.cuh): reciprocal direction, valid only for sane components
-	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
-	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
-		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
 	unsigned cand = 0;               // meshes of the run this lane still has to enter (bit m - p0)
 	unsigned bvhMask = 0;            // meshes of the run that have a root box
 	const float rayT0 = rayT;
@@ -276,6 +275,10 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
 	bool found = false;
 	int p = 0;
+	// exact-filtered slab test (agpt_device.cuh): reciprocal direction, valid only for sane components
+	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
+	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
+		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
 	while (p < sc.n_prims) {
 		agpt_prim prim = sc.prims[p];
 		bool test = lane && !(ANY && found);
@@ -284,6 +287,29 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 			// a run of spheres with consecutive payloads: straight through the sphere table
 			const int len = sc.sphereRun[p];
 			const agpt_sphere* sp = sc.spheres + prim.payload;
+			if (len >= AGPT_RUN_CULL_MIN) {
+				// Exact cull of the whole run: its spheres sit in a box grown by 5 % of the smallest
+				// radius.  A ray that certainly misses that box passes every sphere at more than
+				// r + 0.05 r, and as long as the origin is near enough (runBox.w: |oc|^2 below
+				// ~1e5 r^2) the rounding of Sphere::Intersect's discriminant, ~1e-6 |oc|^2, is far
+				// too small to turn such a miss into a hit.  If no lane of the warp can hit the
+				// box the run is skipped; the reference's test count is kept.
+				const float4 b0 = __ldg(sc.sphereRunBox + 3 * p), b1 = __ldg(sc.sphereRunBox + 3 * p + 1), b2 = __ldg(sc.sphereRunBox + 3 * p + 2);
+				bool maybe = test;
+				if (test && filterOk) {
+					float3 oc = O - f3(b2.x, b2.y, b2.z);
+					if (sqrLength(oc) < b2.w) {
+						float tn, tx;
+						SlabApprox(f3(b0.x, b0.y, b0.z), f3(b0.w, b1.x, b1.y), O, rD, rayT, tn, tx);
+						maybe = SlabDecision(tn, tx) != 0;
+					}
+				}
+				if (!__any_sync(0xffffffffu, maybe)) {
+					if (COUNT && test) cnt.analytic_tests += (unsigned long long)len;
+					p += len;
+					continue;
+				}
+			}
 			for (int j = 0; j < len; j++) {
 				bool tj = test && !(ANY && found);
 				if (COUNT && tj) cnt.analytic_tests++;
@@ -307,7 +333,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 		else {
 			int q = p + 1;                                     // run of consecutive mesh primitives (<= 32 per call)
 			while (q < sc.n_prims && q < p + 32 && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
-			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rD, filterOk, rayT, hit, stack, stackStride, cnt, test)) found = true;
 			p = q;
 		}
 	}
