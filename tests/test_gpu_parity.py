@@ -64,3 +64,30 @@ def test_ray_accounting_matches_reference(agpt, gpu_ctx, config, level, W, H):
     assert st.rays_shadow == cnt["rays_any"]
     assert st.rays_closest + st.rays_mis + st.rays_mis_culled + st.rays_tail_culled == cnt["rays_closest"]
     assert st.rays_reference_equivalent == cnt["rays_closest"] + cnt["rays_any"]
+
+
+def test_sphere_run_cull_is_exact(agpt, ref, gpu_ctx):
+    """The trace kernels skip a whole run of sphere primitives when no ray of a warp can reach the
+    run's (grown) bounding box.  Rays aimed at and around cfg 3's 5x5 sphere grid, from origins a
+    few units to several hundred units away (beyond the distance the cull trusts itself), must
+    give the reference's hits bit for bit, closest-hit and any-hit."""
+    hs = agpt.HostScene(3, 2); rs = ref.RefScene(3, 2)
+    hs.upload(gpu_ctx)
+    rng = np.random.default_rng(20261018)
+    n = 120_000
+    # targets: inside and just outside the slab the sphere grid occupies (centres -3..3 x -0.5 x -4..2, r = 0.5)
+    tgt = np.stack([rng.uniform(-3.7, 3.7, n), rng.uniform(-1.15, 0.15, n), rng.uniform(-4.7, 2.7, n)], 1)
+    dist = rng.choice([2.0, 8.0, 40.0, 150.0, 400.0], n)
+    dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[:, 1] = np.abs(dirs[:, 1]) * rng.choice([1.0, 0.02], n)          # from above, many at grazing angles
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    org = tgt + dirs * dist[:, None]
+    rays = np.concatenate([org, -dirs, np.full((n, 1), 3.0e38)], 1).astype(np.float32)
+    for any_hit in (False, True):
+        want, st = rs.trace_rays(rays, any_hit=any_hit)
+        got = gpu_ctx.trace_rays(rays, any_hit=any_hit)
+        assert np.array_equal(got["found"], want["found"])
+        if not any_hit:
+            assert np.array_equal(got["prim"], want["prim"])
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    assert 0.2 < want["found"].mean() < 1.0
