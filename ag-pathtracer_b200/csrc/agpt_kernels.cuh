@@ -477,6 +477,9 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 #ifndef AGPT_SHADE_THREADS
 #define AGPT_SHADE_THREADS 768
 #endif
+#ifndef AGPT_SHADE_MIN_BLOCKS
+#define AGPT_SHADE_MIN_BLOCKS 1
+#endif
 
 #ifndef AGPT_SHADE_PHASE_SYNC
 #define AGPT_SHADE_PHASE_SYNC 0      // block barrier before each phase (every thread of a block reaches them)
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 #endif
 
 template <bool ENV>
-__global__ void __launch_bounds__(AGPT_SHADE_THREADS, 1) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
+__global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
 	const int count = *sp.count;
 	// one block-sized piece of the list per block, no loop: warps that start together stay together
