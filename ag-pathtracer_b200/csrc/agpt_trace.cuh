@@ -293,7 +293,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 				// r + 0.05 r, and as long as the origin is near enough (runBox.w: |oc|^2 below
 				// ~1e5 r^2) the rounding of Sphere::Intersect's discriminant, ~1e-6 |oc|^2, is far
 				// too small to turn such a miss into a hit.  If no lane of the warp can hit the
-				// box the run is skipped; the reference's test count is kept.
+				// box the run is skipped (analytic_tests counts the records really read).
 				const float4 b0 = __ldg(sc.sphereRunBox + 3 * p), b1 = __ldg(sc.sphereRunBox + 3 * p + 1), b2 = __ldg(sc.sphereRunBox + 3 * p + 2);
 				bool maybe = test;
 				if (test && filterOk) {
@@ -304,11 +304,8 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 						maybe = SlabDecision(tn, tx) != 0;
 					}
 				}
-				if (!__any_sync(0xffffffffu, maybe)) {
-					if (COUNT && test) cnt.analytic_tests += (unsigned long long)len;
-					p += len;
-					continue;
-				}
+				if (COUNT && test) cnt.analytic_tests++;          // the box record counts as one analytic record read
+				if (!__any_sync(0xffffffffu, maybe)) { p += len; continue; }
 			}
 			for (int j = 0; j < len; j++) {
 				bool tj = test && !(ANY && found);
