@@ -70,6 +70,7 @@ struct agpt_ctx {
 	DevBuf<float4> sphereRunBox;
 	std::vector<agpt_sphere> hostSpheres;
 	bool runsDirty = true;
+	int maxSphereRun = 1 << 20;   // AGPT_MAX_SPHERE_RUN
 	DevBuf<agpt_material> mats;
 	DevBuf<agpt_light> lights;
 	DevBuf<float> envRgb, envFunc, envCdf;
@@ -126,7 +127,7 @@ static int BuildSphereRuns(agpt_ctx* c) {
 	for (int p = n - 1; p >= 0; p--) {
 		if (rows[p].type != AGPT_PRIM_SPHERE) continue;
 		bool chained = p + 1 < n && rows[p + 1].type == AGPT_PRIM_SPHERE && rows[p + 1].payload == rows[p].payload + 1;
-		run[p] = chained ? run[p + 1] + 1 : 1;
+		run[p] = chained && run[p + 1] < c->maxSphereRun ? run[p + 1] + 1 : 1;     // capped: shorter runs have tighter boxes
 	}
 	for (int p = 0; p < n; p++) {
 		if (run[p] == 0) continue;
@@ -291,6 +292,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	if (const char* e = getenv("AGPT_ASYNC_WAVES")) c->asyncWaves = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BATCH_LOG2")) { int b = atoi(e); if (b >= 10 && b <= 28) c->maxPathsPerBatch = (size_t)1 << b; }
 	if (const char* e = getenv("AGPT_BUCKET_CALIBRATE")) c->calibrateGrid = atoi(e) != 0;
+	if (const char* e = getenv("AGPT_MAX_SPHERE_RUN")) { int v = atoi(e); if (v >= 1) c->maxSphereRun = v; }
 	if (const char* e = getenv("AGPT_OVERLAP_ANY")) c->overlapAny = atoi(e) != 0;
 	if (const char* e = getenv("AGPT_BUCKET_RAYS")) c->bucketRays = atoi(e) != 0;
 	*out = c;
