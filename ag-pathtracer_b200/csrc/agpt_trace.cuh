@@ -54,22 +54,7 @@ struct NodeBox {
 	float3 bmin, bmax;
 	int first, count;
 };
-// BVH table loads.  AGPT_L2_KEEP=1 tags them L2::evict_last (createpolicy + cache_hint) so the
-// trees outlive the path-state streams in L2.
-#ifndef AGPT_L2_KEEP
-#define AGPT_L2_KEEP 0
-#endif
-__device__ __forceinline__ float4 LoadTable(const float4* __restrict__ p) {
-#if AGPT_L2_KEEP
-	unsigned long long pol;
-	asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-	float4 v;
-	asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-	return v;
-#else
-	return __ldg(p);
-#endif
-}
+__device__ __forceinline__ float4 LoadTable(const float4* __restrict__ p) { return __ldg(p); }
 __device__ __forceinline__ NodeBox LoadNode(const float4* __restrict__ nodes, int i) {
 	float4 a = LoadTable(nodes + 2 * i), b = LoadTable(nodes + 2 * i + 1);
 	NodeBox n;
@@ -99,9 +84,6 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 #endif
 #ifndef AGPT_RUN_CULL_MIN
 #define AGPT_RUN_CULL_MIN 4        // sphere runs at least this long get a bounding-box pre-test
-#endif
-#ifndef AGPT_PREFETCH_TRI
-#define AGPT_PREFETCH_TRI 0      // prefetch the triangle of a single-triangle leaf as soon as the walk decides to visit it next
 #endif
 
 // A RUN of at most 32 consecutive mesh primitives [p0, p1) of Scene::primitives.  `stack` points
@@ -222,13 +204,6 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						pop = false;
 					}
 					else if (hl || hr) { cur = hl ? el : er; pop = false; }
-#if AGPT_PREFETCH_TRI
-					if (!pop && (cur & AGPT_ENT_LEAF1)) {
-						const float4* tp = tris + 3 * (int)(cur & 0x7fffffffu);
-						asm volatile("prefetch.global.L1 [%0];" :: "l"(tp));
-						asm volatile("prefetch.global.L1 [%0];" :: "l"(tp + 2));
-					}
-#endif
 				}
 				else {
 					int first, count;
