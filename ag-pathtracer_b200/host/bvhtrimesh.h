@@ -267,7 +267,7 @@ private:
 			for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, b + i, 8); h = (h ^ w) * 1099511628211ull; }
 			for (; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
 		};
-		mix(vertices.data(), vertices.size() * sizeof(vertices[0]));
+		for (const auto& v : vertices) { float xyz[3] = { v.x, v.y, v.z }; mix(xyz, sizeof(xyz)); }      // (not the float3's padding lane)
 		for (const auto& ix : indices) { int v = ix.vertex_index; mix(&v, sizeof(v)); }
 		mix(&maxPrims, sizeof(maxPrims));
 		return h;

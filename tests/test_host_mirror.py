@@ -104,6 +104,7 @@ def test_bvh_cache_round_trip_and_damage(agpt, tmp_path):
         files = sorted(tmp_path.glob("*.agbvh"))
         assert len(files) >= 1 and not list(tmp_path.glob("*.tmp*"))
         cached = _all_bvhs(agpt.HostScene(3, 4))             # reads them back
+        assert sorted(tmp_path.glob("*.agbvh")) == files, "the mesh key must not depend on padding bytes: same scene, same files"
         for (n0, o0), (n1, o1), (n2, o2) in zip(fresh, built, cached):
             assert np.array_equal(n0, n1) and np.array_equal(o0, o1)
             assert np.array_equal(n0, n2) and np.array_equal(o0, o2)
