@@ -146,10 +146,13 @@ static int BuildSphereRuns(agpt_ctx* c) {
 		const float grow = 0.05f * rmin;
 		float ctr[3], diag2 = 0.f;
 		for (int a = 0; a < 3; a++) { lo[a] -= grow; hi[a] += grow; ctr[a] = 0.5f * (lo[a] + hi[a]); float h = 0.5f * (hi[a] - lo[a]); diag2 += h * h; }
-		// |O - C_sphere|^2 <= 2 (|O - ctr|^2 + diag2) must stay below 1e5 rmin^2
+		// Rounding of Sphere::Intersect's discriminant is at most ~22 * 2^-24 |oc|^2 = 1.3e-6 |oc|^2 (every
+		// product, sum and input rounding counted against us); a ray that misses the grown box has
+		// d^2 - r^2 > 2 r grow = 0.1 rmin^2.  With |oc|^2 <= 2 (|O - ctr|^2 + diag2) kept below 2e4 rmin^2 the
+		// rounding stays under 0.026 rmin^2: a factor 4 of slack on a worst-case bound.
 		b[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
 		b[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
-		b[2] = make_float4(ctr[0], ctr[1], ctr[2], 0.5e5f * rmin * rmin - diag2);
+		b[2] = make_float4(ctr[0], ctr[1], ctr[2], 1.0e4f * rmin * rmin - diag2);
 	}
 	CU(c->sphereRun.Upload(run.data(), (size_t)n, c->stream));
 	CU(c->sphereRunBox.Upload(box.data(), box.size(), c->stream));

@@ -298,7 +298,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 					// Exact cull of the whole run: its spheres sit in a box grown by 5 % of the smallest
 					// radius.  A ray that certainly misses that box passes every sphere at more than
 					// r + 0.05 r, and as long as the origin is near enough (runBox.w: |oc|^2 below
-					// ~1e5 r^2) the rounding of Sphere::Intersect's discriminant, ~1e-6 |oc|^2, is far
+					// 2e4 r^2) the rounding of Sphere::Intersect's discriminant, < 1.3e-6 |oc|^2, is far
 					// too small to turn such a miss into a hit.  If no lane of the warp can hit the
 					// box the run is skipped (analytic_tests counts the records really read).
 					const float4 b0 = __ldg(sc.sphereRunBox + 3 * p), b1 = __ldg(sc.sphereRunBox + 3 * p + 1), b2 = __ldg(sc.sphereRunBox + 3 * p + 2);
