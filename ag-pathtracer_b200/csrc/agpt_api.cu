@@ -223,6 +223,13 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 		NEED(l.type != AGPT_LIGHT_INFINITE_AREA || c->envW > 0, AGPT_ERR_STATE, "InfiniteAreaLight without an environment map (agpt_upload_envmap)");
 	for (auto& l : c->hostLights)
 		NEED(l.type != AGPT_LIGHT_AREA || (l.prim >= 0 && l.prim < (int)c->hostPrims.size()), AGPT_ERR_INVALID, "area light without a primitive");
+	// An AreaLight wraps exactly one shape upstream (scene.h addAreaLight; lights.h:70-86), and the exact
+	// MIS-ray cull relies on it: the primitive a light names must be the only one that names the light.
+	for (size_t i = 0; i < c->hostPrims.size(); i++) {
+		int al = c->hostPrims[i].area_light;
+		NEED(al < 0 || (c->hostLights[al].type == AGPT_LIGHT_AREA && c->hostLights[al].prim == (int)i), AGPT_ERR_INVALID,
+			"primitive and area light do not name each other (one shape per AreaLight)");
+	}
 	if (c->runsDirty) {
 		CU(cudaSetDevice(c->device));
 		int rcode = BuildSphereRuns(c);

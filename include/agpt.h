@@ -85,7 +85,8 @@ typedef struct agpt_prim {
 	int32_t type;        /* AGPT_PRIM_* */
 	int32_t payload;     /* index into the spheres / planes / meshes table of that type */
 	int32_t material;    /* index into materials, -1 = nullptr material (emissive shape, integrator.h:152-161) */
-	int32_t area_light;  /* index into lights of the AreaLight wrapping this shape, -1 = none */
+	int32_t area_light;  /* index into lights of the AreaLight wrapping this shape, -1 = none; that light's
+	                        `prim` must be this row (one shape per AreaLight, as upstream), else AGPT_ERR_INVALID */
 } agpt_prim;
 
 enum { AGPT_MAT_DISNEY = 1, AGPT_MAT_MIRROR = 2 };
