@@ -53,7 +53,7 @@ struct alignas(16) float3 {
 	float3() = default;
 	float3(float a, float b, float c) : x(a), y(b), z(c) {}
 	float3(float a) : x(a), y(a), z(a) {}
-	float x, y, z, dummy;
+	float x, y, z, dummy = 0.f;     // (upstream leaves the padding lane uninitialised; nothing may depend on it)
 	float operator[](int n) const { return (&x)[n]; }
 };
 
