@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 FLAG_COUNTERS = 1
 FLAG_TIMING = 2
 FLAG_STRICT_BOXES = 4
+FLAG_RAYS_FINAL = 8
 
 MAT_DISNEY = 1
 MAT_MIRROR = 2
@@ -200,12 +201,12 @@ class Context:
         _check(core().agpt_li_pixels(self._h, c_int(len(xs)), ip(xs), ip(ys), ip(ss), c_int(max_depth), c_int(depth_arg), _fptr(out)))
         return out
 
-    def li_rays(self, rays7, rng_states, max_depth, depth_arg=0):
+    def li_rays(self, rays7, rng_states, max_depth, depth_arg=0, flags=0):
         rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
         rng_states = np.ascontiguousarray(rng_states, np.uint32)
         out = np.empty((len(rays7), 3), np.float32)
         _check(core().agpt_li_rays(self._h, c_int(len(rays7)), _fptr(rays7), rng_states.ctypes.data_as(POINTER(c_uint32)),
-                                   c_int(max_depth), c_int(depth_arg), _fptr(out)))
+                                   c_int(max_depth), c_int(depth_arg), c_uint32(flags), _fptr(out)))
         return out
 
     def stats(self):
@@ -215,6 +216,11 @@ class Context:
 
     def reset_stats(self):
         _check(core().agpt_reset_stats(self._h))
+
+    def debug_status(self):
+        out = (c_uint64 * 4)()
+        _check(core().agpt_debug_status(self._h, out))
+        return dict(failed=out[0], first_code=out[1], first_value=out[2], checks=out[3])
 
     def scene_bytes(self):
         b = c_uint64(0)

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "agpt_kernels.cuh"
@@ -58,6 +59,7 @@ struct agpt_ctx {
 	cudaStream_t sideStream = nullptr;   // any-hit trace of a wave runs here, beside the closest-hit trace
 	cudaEvent_t evFork = nullptr, evJoin = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
+	cudaEvent_t evRender0 = nullptr, evRender1 = nullptr;      // bracket of agpt_render (ms_render)
 	int smCount = 0;
 
 	// scene tables
@@ -79,6 +81,7 @@ struct agpt_ctx {
 	std::vector<agpt_prim> hostPrims;
 	std::vector<agpt_light> hostLights;
 	int nMeshes = 0, nSpheres = 0, nPlanes = 0, nMats = 0;
+	int maxBvhDepth = 0;          // deepest uploaded tree (levels below the root), validated against the traversal stack
 	agpt_camera cam;
 	bool haveCam = false;
 	float boundsLo[3] = { -1, -1, -1 }, boundsHi[3] = { 1, 1, 1 };   // bounded geometry (mesh roots), for ray bucketing only
@@ -89,6 +92,7 @@ struct agpt_ctx {
 
 	// film
 	DevBuf<float4> accumOwn;
+	DevBuf<uint32_t> resolved;    // agpt_resolve's packed output, kept between calls
 	float4* accum = nullptr;      // accumOwn.p or caller-owned
 
 	// wavefront state
@@ -184,11 +188,13 @@ static PathState MakePathState(agpt_ctx* c) {
 	p.shO = c->f4[8].p; p.shD = c->f4[9].p; p.misO = c->f4[10].p; p.misD = c->f4[11].p; p.Lout = c->f4[12].p;
 	p.hitSlot = c->i32[0].p; p.shadowOccluded = c->i32[1].p; p.misPrim = c->i32[2].p;
 	p.rng = c->u32[0].p; p.flags = c->u32[1].p;
+	p.slots = (int)c->capacity;
 	return p;
 }
 
 static int EnsureCapacity(agpt_ctx* c, size_t paths) {
 	if (paths <= c->capacity) return AGPT_OK;
+	c->capacity = 0;                 // published again only when every buffer below is there (a failed allocation must not leave a stale size)
 	for (auto& b : c->f4) CU(b.Alloc(paths));
 	for (auto& b : c->i32) CU(b.Alloc(paths));
 	for (auto& b : c->u32) CU(b.Alloc(paths));
@@ -229,6 +235,14 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 		int al = c->hostPrims[i].area_light;
 		NEED(al < 0 || (c->hostLights[al].type == AGPT_LIGHT_AREA && c->hostLights[al].prim == (int)i), AGPT_ERR_INVALID,
 			"primitive and area light do not name each other (one shape per AreaLight)");
+	}
+	if (c->mats.p == nullptr) {
+		// a scene of null-material (emissive) shapes only is legal upstream; shade still needs a record to point idle lanes at
+		CU(cudaSetDevice(c->device));
+		agpt_material none;
+		memset(&none, 0, sizeof(none));
+		CU(c->mats.Upload(&none, 1, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
 	}
 	if (c->runsDirty) {
 		CU(cudaSetDevice(c->device));
@@ -290,6 +304,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
+	CU(cudaEventCreate(&c->evRender0)); CU(cudaEventCreate(&c->evRender1));
 	CU(c->counts.Alloc(6));
 	CU(c->survivorCount.Alloc(1));
 	CU(c->hist.Alloc(3 * AGPT_BUCKETS));
@@ -315,7 +330,7 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	for (auto& m : c->meshStore) m.Free();
 	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
-	c->accumOwn.Free();
+	c->accumOwn.Free(); c->resolved.Free();
 	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
 	for (auto& b : c->i32) b.Free();
@@ -328,6 +343,7 @@ int agpt_destroy(agpt_ctx* c) {
 	if (c->hostCounts) cudaFreeHost(c->hostCounts);
 	for (auto& e : c->ringEvents) if (e) cudaEventDestroy(e);
 	cudaEventDestroy(c->evA); cudaEventDestroy(c->evB); cudaEventDestroy(c->evC); cudaEventDestroy(c->evD);
+	cudaEventDestroy(c->evRender0); cudaEventDestroy(c->evRender1);
 	cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin);
 	cudaStreamDestroy(c->sideStream);
 	cudaStreamDestroy(c->ownStream);
@@ -344,18 +360,70 @@ int agpt_set_stream(agpt_ctx* c, void* s) {
 }
 
 // ---- scene upload ------------------------------------------------------------------------
+// One pass over a caller-supplied node table before anything is uploaded: every interior link and
+// leaf range must stay inside its table, the links must form a TREE (a child reached twice -- a
+// shared child or a link back to an ancestor -- would make the walk loop or double-count), and the
+// tree must not be deeper than the traversal stack.  The reference recurses without a limit
+// (bvhtrimesh.h:332-413); the device stack holds AGPT_STACK_SMEM + AGPT_STACK_LOCAL far children,
+// far more than any SAH tree over 2^31 triangles needs, and deeper tables are refused here
+// instead of corrupting memory there.
+static int ValidateBvh(const agpt_mesh_desc& d, int meshIndex, int* depthOut) {
+	*depthOut = 0;
+	if (d.n_nodes == 0) return AGPT_OK;
+	const std::string where = "mesh " + std::to_string(meshIndex) + ": ";
+	NEED(d.n_nodes == 1 || d.n_nodes >= 3, AGPT_ERR_INVALID, where + "node table of 2 entries (root at 0, slot 1 unused, children from 2)");
+	std::vector<unsigned char> seen((size_t)d.n_nodes, 0);
+	std::vector<std::pair<int, int>> todo;      // node, depth
+	todo.emplace_back(0, 0);
+	seen[0] = 1;
+	int maxDepth = 0;
+	while (!todo.empty()) {
+		auto [k, depth] = todo.back();
+		todo.pop_back();
+		const agpt_bvh_node& nd = d.nodes[k];
+		if (depth > maxDepth) maxDepth = depth;
+		if (nd.count > 0) {
+			NEED(nd.first >= 0 && (long long)nd.first + nd.count <= d.n_tris, AGPT_ERR_INVALID, where + "BVH leaf range outside the triangle table");
+			continue;
+		}
+		NEED(nd.count == 0, AGPT_ERR_INVALID, where + "BVH node with a negative count");
+		NEED(nd.first >= 2 && nd.first + 1 < d.n_nodes, AGPT_ERR_INVALID, where + "BVH child link outside the node table");
+		NEED(!seen[nd.first] && !seen[nd.first + 1], AGPT_ERR_INVALID, where + "BVH node table is not a tree (a child is linked twice, or links back to an ancestor)");
+		seen[nd.first] = seen[nd.first + 1] = 1;
+		NEED(depth + 1 <= AGPT_STACK_SMEM + AGPT_STACK_LOCAL, AGPT_ERR_INVALID,
+			where + "BVH deeper than " + std::to_string(AGPT_STACK_SMEM + AGPT_STACK_LOCAL) + " levels (the device traversal stack)");
+		todo.emplace_back(nd.first, depth + 1);
+		todo.emplace_back(nd.first + 1, depth + 1);
+	}
+	*depthOut = maxDepth;
+	return AGPT_OK;
+}
+
 int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	NEED(c != nullptr && n >= 0 && (n == 0 || meshes != nullptr), AGPT_ERR_INVALID, "bad mesh table");
-	CU(cudaSetDevice(c->device));
-	CU(cudaStreamSynchronize(c->stream));
-	c->gridCalibrated = false;
-	for (auto& m : c->meshStore) m.Free();
-	c->meshStore.assign(n, MeshStore());
-	std::vector<DMesh> table(n);
+	// validate every descriptor before touching what is resident: a refused upload leaves the old scene intact
+	int maxDepth = 0;
 	for (int i = 0; i < n; i++) {
 		const agpt_mesh_desc& d = meshes[i];
 		NEED(d.n_tris >= 0 && d.n_nodes >= 0 && (d.n_tris == 0 || (d.tri_verts && d.tri_ids)), AGPT_ERR_INVALID, "mesh without triangle data");
-		NEED(d.n_nodes == 0 || (d.nodes != nullptr && d.n_nodes >= 1), AGPT_ERR_INVALID, "mesh node table missing");
+		NEED(d.n_nodes == 0 || d.nodes != nullptr, AGPT_ERR_INVALID, "mesh node table missing");
+		int depth = 0;
+		int rcode = ValidateBvh(d, i, &depth);
+		if (rcode != AGPT_OK) return rcode;
+		if (depth > maxDepth) maxDepth = depth;
+	}
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	c->gridCalibrated = false;
+	// from here on a failure must not leave the device table pointing at freed buffers
+	for (auto& m : c->meshStore) m.Free();
+	c->meshStore.assign(n, MeshStore());
+	c->meshes.Free();
+	c->nMeshes = 0;
+	c->maxBvhDepth = 0;
+	std::vector<DMesh> table(n);
+	for (int i = 0; i < n; i++) {
+		const agpt_mesh_desc& d = meshes[i];
 		MeshStore& st = c->meshStore[i];
 		CU(st.nodes.Upload((const float4*)d.nodes, 2 * (size_t)d.n_nodes, c->stream));
 		CU(st.tris.Upload((const float4*)d.tri_verts, 3 * (size_t)d.n_tris, c->stream));
@@ -367,13 +435,6 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 			CU(cudaGetLastError());
 			c->stats.kernel_launches++;
 		}
-		// interior links and leaf ranges must stay inside the tables
-		for (int k = 0; k < d.n_nodes; k++) {
-			if (k == 1) continue;
-			const agpt_bvh_node& nd = d.nodes[k];
-			if (nd.count > 0) NEED(nd.first >= 0 && nd.first + nd.count <= d.n_tris, AGPT_ERR_INVALID, "BVH leaf range outside the triangle table");
-			else NEED(nd.first >= 2 && nd.first + 1 < d.n_nodes, AGPT_ERR_INVALID, "BVH child link outside the node table");
-		}
 		DMesh& m = table[i];
 		m.nodes = st.nodes.p; m.tris = st.tris.p; m.ids = st.ids.p; m.normals = st.normals.p; m.uvs = st.uvs.p;
 		m.n_nodes = d.n_nodes; m.n_tris = d.n_tris;
@@ -381,6 +442,7 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	CU(c->meshes.Upload(table.data(), (size_t)n, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	c->nMeshes = n;
+	c->maxBvhDepth = maxDepth;
 	bool any = false;
 	for (int i = 0; i < n; i++) {
 		if (meshes[i].n_nodes == 0) continue;
@@ -509,14 +571,12 @@ int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
 	NEED(c != nullptr && host != nullptr && c->accum != nullptr && samples > 0, AGPT_ERR_STATE, "film not set or samples <= 0");
 	CU(cudaSetDevice(c->device));
 	int n = c->width * c->height;
-	DevBuf<uint32_t> out;
-	CU(out.Alloc(n));
-	k_resolve<<<Blocks(n, 256), 256, 0, c->stream>>>(c->accum, out.p, n, (float)samples);
+	if (c->resolved.n != (size_t)n) CU(c->resolved.Alloc(n));
+	k_resolve<<<Blocks(n, 256), 256, 0, c->stream>>>(c->accum, c->resolved.p, n, (float)samples);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
-	CU(cudaMemcpyAsync(host, out.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(host, c->resolved.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
-	out.Free();
 	return AGPT_OK;
 }
 
@@ -727,8 +787,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	WaveQueues q0;
 	q0.closest = c->queues[0].p; q0.shadow = c->queues[2].p; q0.active = c->queues[4].p; q0.counts = c->counts.p; q0.keys = nullptr; q0.shadowKeys = nullptr;
 	// evA/evC/evD are reused inside RunWaves when timing; the render bracket has its own pair
-	cudaEvent_t r0, r1;
-	CU(cudaEventCreate(&r0)); CU(cudaEventCreate(&r1));
+	cudaEvent_t r0 = c->evRender0, r1 = c->evRender1;
 	CU(cudaEventRecord(r0, c->stream));
 	for (int done = 0; done < num_samples; done += perBatch) {
 		int ns = num_samples - done < perBatch ? num_samples - done : perBatch;
@@ -742,7 +801,7 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 		c->stats.paths += (uint64_t)n;
 		c->stats.rays_closest += (uint64_t)n;     // camera rays; the rest is counted on the device
 		rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, flags);
-		if (rcode != AGPT_OK) { cudaEventDestroy(r0); cudaEventDestroy(r1); return rcode; }
+		if (rcode != AGPT_OK) return rcode;
 		k_accumulate<<<Blocks(wh, 256), 256, 0, c->stream>>>(ps.Lout, c->accum, c->width, c->height, ns);
 		CU(cudaGetLastError());
 		c->stats.kernel_launches++;
@@ -751,7 +810,6 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 	CU(cudaStreamSynchronize(c->stream));
 	float ms = 0;
 	cudaEventElapsedTime(&ms, r0, r1);
-	cudaEventDestroy(r0); cudaEventDestroy(r1);
 	c->stats.ms_render += ms;
 	return AGPT_OK;
 }
@@ -812,7 +870,7 @@ int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uin
 	CU(cudaMemsetAsync(seeds.p, 0, seeds.Bytes(), c->stream));
 	GenParams g;
 	memset(&g, 0, sizeof(g));
-	g.n = (int)n; g.rays7 = rays.p; g.seeds = seeds.p;
+	g.n = (int)n; g.rays7 = rays.p; g.seeds = seeds.p; g.raysFinal = (flags & AGPT_FLAG_RAYS_FINAL) ? 1 : 0;
 	k_generate<<<Blocks(n, 256), 256, 0, c->stream>>>(sc, ps, q0, g);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
@@ -859,7 +917,7 @@ int agpt_li_pixels(agpt_ctx* c, int n, const int* xs, const int* ys, const int* 
 	return rcode;
 }
 
-int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_states, int max_depth, int rr_depth_arg, float* out_rgb) {
+int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_states, int max_depth, int rr_depth_arg, uint32_t flags, float* out_rgb) {
 	int rcode = CheckReady(c, false);
 	if (rcode != AGPT_OK) return rcode;
 	NEED(n >= 0 && (n == 0 || (rays7 && rng_states && out_rgb)), AGPT_ERR_INVALID, "bad ray list");
@@ -871,7 +929,7 @@ int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_sta
 	CU(seeds.Upload(rng_states, (size_t)n, c->stream));
 	GenParams g;
 	memset(&g, 0, sizeof(g));
-	g.n = n; g.rays7 = rays.p; g.seeds = seeds.p;
+	g.n = n; g.rays7 = rays.p; g.seeds = seeds.p; g.raysFinal = (flags & AGPT_FLAG_RAYS_FINAL) ? 1 : 0;
 	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
 	rays.Free(); seeds.Free();
 	return rcode;
@@ -906,6 +964,18 @@ int agpt_get_stats(agpt_ctx* c, agpt_stats* out) {
 	out->ms_other = out->ms_render - out->ms_trace_closest - out->ms_trace_any - out->ms_shade;
 	return AGPT_OK;
 }
+int agpt_debug_status(agpt_ctx* c, uint64_t* out4) {
+	NEED(c != nullptr && out4 != nullptr, AGPT_ERR_INVALID, "null argument");
+	out4[0] = out4[1] = out4[2] = out4[3] = 0;
+#ifdef AGPT_DEBUG
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	unsigned long long v[4];
+	CU(cudaMemcpyFromSymbol(v, g_agptDebug, sizeof(v)));
+	for (int k = 0; k < 4; k++) out4[k] = v[k];
+#endif
+	return AGPT_OK;
+}
 int agpt_reset_stats(agpt_ctx* c) {
 	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
 	CU(cudaSetDevice(c->device));
@@ -930,6 +1000,8 @@ __global__ void k_probe_bounds(int n, const float* boxes6, const float* rays7, i
 	out_t[i] = h ? t : 0.f;
 }
 
+// BSDF::f / Pdf / Sample_f through the SAME functions k_shade_b runs (VertexBsdfInit, EvalLobes,
+// FinishEval, SampleLobeDir, FinishSample), against golden vectors of the reference's own methods.
 __global__ void k_probe_bsdf(int n, agpt_material mat, const float* in14, int skipSpecular, float* out12) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -938,16 +1010,31 @@ __global__ void k_probe_bsdf(int n, agpt_material mat, const float* in14, int sk
 	float2 u = make_float2(a[12], a[13]);
 	DSurface si;
 	SurfaceInit(si, f3(0.f), dpdu, dpdv);
-	DBSDF bsdf = MakeBSDF(si, &mat);
+	VertexBsdf vb;
+	VertexBsdfInit(vb, si, &mat, wo);
 	float* o = out12 + 12 * i;
-	float3 f = BSDF_f(bsdf, wo, wi, skipSpecular != 0);
-	o[0] = f.x; o[1] = f.y; o[2] = f.z;
-	o[3] = BSDF_Pdf(bsdf, wo, wi, skipSpecular != 0);
-	float3 wis = f3(0.f);
-	float pdf = 0;
-	bool spec = false;
-	float3 fs = BSDF_Sample_f(bsdf, wo, &wis, u, &pdf, skipSpecular != 0, &spec);
-	o[4] = wis.x; o[5] = wis.y; o[6] = wis.z; o[7] = fs.x; o[8] = fs.y; o[9] = fs.z; o[10] = pdf; o[11] = spec ? 1.f : 0.f;
+	// f(wo, wi) and Pdf(wo, wi): zero when wo.z == 0 (reflection.h:117,178)
+	float3 f = f3(0.f);
+	float pdf = 0.f;
+	LobeEval ev;
+	if (vb.woOk) {
+		EvalLobes(vb, WorldToLocal(vb.b, wi), ev);
+		f = FinishEval(vb, ev, wi, &pdf);
+	}
+	o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = pdf;
+	// Sample_f(wo, &wi, u, &pdf, skipSpecular, &sampledSpecular)
+	DirSample smp;
+	SampleLobeDir(vb, u, skipSpecular != 0, smp);
+	float3 wis = f3(0.f), fs = f3(0.f);
+	float pdfs = 0.f;
+	if (smp.ok) {
+		ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
+		if (smp.lobe != AGPT_LOBE_SPECULAR) EvalLobes(vb, smp.wi, ev);
+		wis = LocalToWorld(vb.b, smp.wi);
+		fs = FinishSample(vb, smp, ev, wis, &pdfs);
+	}
+	bool spec = vb.woOk && smp.matching > 0 && smp.lobe == AGPT_LOBE_SPECULAR;
+	o[4] = wis.x; o[5] = wis.y; o[6] = wis.z; o[7] = fs.x; o[8] = fs.y; o[9] = fs.z; o[10] = pdfs; o[11] = spec ? 1.f : 0.f;
 }
 
 __global__ void k_probe_sphere_sample(int n, const float* in9, float* out8) {

@@ -97,9 +97,6 @@ __device__ __forceinline__ float TR_Lambda(float ax, float ay, float3 w) {
 	return (-1 + sqrtf(1.f + alpha2Tan2Theta)) / 2;
 }
 __device__ __forceinline__ float TR_G1(float ax, float ay, float3 w) { return 1 / (1 + TR_Lambda(ax, ay, w)); }
-__device__ __forceinline__ float TR_Pdf(float ax, float ay, float3 wo, float3 wh) {
-	return TR_D(ax, ay, wh) * TR_G1(ax, ay, wo) * absdot(wo, wh) / AbsCosTheta(wo);
-}
 __device__ __forceinline__ void TrowbridgeReitzSample11(float cosTheta, float U1, float U2, float* slope_x, float* slope_y) {
 	if (cosTheta > .9999f) {
 		float r = sqrtf(U1 / (1 - U1));
@@ -147,37 +144,7 @@ __device__ __forceinline__ float3 TR_Sample_wh(float ax, float ay, float3 wo, fl
 	return wh;
 }
 
-// ---------------------------------------------------------------------------------------
-// lobes (disney.h:24-60, reflection.h:5-78, reflection.cpp:13-17)
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float3 DisneyDiffuse_f(const agpt_material& m, float3 wo, float3 wi) {
-	float Fo = SchlickWeight(AbsCosTheta(wo)), Fi = SchlickWeight(AbsCosTheta(wi));
-	return f3(m.diffuse_r) * AGPT_INVPI * (1 - Fo / 2) * (1 - Fi / 2);
-}
-__device__ __forceinline__ float3 DisneyRetro_f(const agpt_material& m, float3 wo, float3 wi) {
-	float3 wh = wi + wo;
-	if (wh.x == 0 && wh.y == 0 && wh.z == 0) return f3(0.f);
-	wh = normalize(wh);
-	float cosThetaD = dot(wi, wh);
-	float Fo = SchlickWeight(AbsCosTheta(wo)), Fi = SchlickWeight(AbsCosTheta(wi));
-	float Rr = 2 * m.roughness * cosThetaD * cosThetaD;
-	return f3(m.diffuse_r) * AGPT_INVPI * Rr * (Fo + Fi + Fo * Fi * (Rr - 1));
-}
-__device__ __forceinline__ float3 Microfacet_f(const agpt_material& m, float3 wo, float3 wi) {
-	float cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
-	float3 wh = wi + wo;
-	if (cosThetaI == 0 || cosThetaO == 0) return f3(0.f);
-	if (wh.x == 0 && wh.y == 0 && wh.z == 0) return f3(0.f);
-	wh = normalize(wh);
-	float3 F = DisneyFresnel(m, dot(wi, Faceforward(wh, f3(0, 0, 1))));
-	float G = TR_G1(m.alpha_x, m.alpha_y, wo) * TR_G1(m.alpha_x, m.alpha_y, wi);
-	return f3(1.f) * TR_D(m.alpha_x, m.alpha_y, wh) * G * F / (4 * cosThetaI * cosThetaO);
-}
-__device__ __forceinline__ float Microfacet_Pdf(const agpt_material& m, float3 wo, float3 wi) {
-	if (!SameHemisphere(wo, wi)) return 0;
-	float3 wh = normalize(wo + wi);
-	return TR_Pdf(m.alpha_x, m.alpha_y, wo, wh) / (4 * dot(wo, wh));
-}
+// BxDF::Pdf of a cosine-sampled lobe (reflection.h:16-18); the lobes' f / Pdf live in EvalLobes below
 __device__ __forceinline__ float Cosine_Pdf(float3 wo, float3 wi) { return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * AGPT_INVPI : 0; }
 
 // lobe order of BSDF::bxdfs[] for a material (material.h:51-58,79-81)
@@ -189,25 +156,10 @@ __device__ __forceinline__ int LobeList(const agpt_material& m, bool skipSpecula
 	if ((m.lobes & AGPT_LOBE_SPECULAR) && !skipSpecular) lobes[n++] = AGPT_LOBE_SPECULAR;
 	return n;
 }
-__device__ __forceinline__ float3 Lobe_f(const agpt_material& m, int lobe, float3 wo, float3 wi) {
-	switch (lobe) {
-	case AGPT_LOBE_DIFFUSE: return DisneyDiffuse_f(m, wo, wi);
-	case AGPT_LOBE_RETRO: return DisneyRetro_f(m, wo, wi);
-	case AGPT_LOBE_MICROFACET: return Microfacet_f(m, wo, wi);
-	default: return f3(0.f);   // SpecularReflection::f (reflection.h:26-28)
-	}
-}
-__device__ __forceinline__ float Lobe_Pdf(const agpt_material& m, int lobe, float3 wo, float3 wi) {
-	switch (lobe) {
-	case AGPT_LOBE_DIFFUSE:
-	case AGPT_LOBE_RETRO: return Cosine_Pdf(wo, wi);
-	case AGPT_LOBE_MICROFACET: return Microfacet_Pdf(m, wo, wi);
-	default: return 0;        // SpecularReflection::Pdf (reflection.h:30)
-	}
-}
 
 // ---------------------------------------------------------------------------------------
-// BSDF (reflection.h:83-201, reflection.cpp:6-11)
+// BSDF (reflection.h:83-201, reflection.cpp:6-11): frame and transforms.  BSDF::f / Pdf /
+// Sample_f themselves are realised by the fused per-vertex evaluator further down.
 // ---------------------------------------------------------------------------------------
 struct DBSDF {
 	float3 ng, ns, ss, ts;
@@ -220,77 +172,6 @@ __device__ __forceinline__ float3 LocalToWorld(const DBSDF& b, float3 v) {
 		b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
 }
 __device__ __forceinline__ bool BSDF_IsPerfectlySpecular(const DBSDF& b) { return (b.mat->lobes & ~AGPT_LOBE_SPECULAR) == 0; }
-
-__device__ __noinline__ float3 BSDF_f(const DBSDF& b, float3 woW, float3 wiW, bool skipSpecular) {
-	float3 wi = WorldToLocal(b, wiW), wo = WorldToLocal(b, woW);
-	if (wo.z == 0) return f3(0.f);
-	bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
-	float3 f = f3(0.f);
-	int lobes[4];
-	int n = LobeList(*b.mat, skipSpecular, lobes);
-	for (int i = 0; i < n; i++)
-		if (reflect) f += Lobe_f(*b.mat, lobes[i], wo, wi);
-	return f;
-}
-__device__ __noinline__ float BSDF_Pdf(const DBSDF& b, float3 woW, float3 wiW, bool skipSpecular) {
-	if (b.mat->lobes == 0) return 0.f;
-	float3 wo = WorldToLocal(b, woW), wi = WorldToLocal(b, wiW);
-	if (wo.z == 0) return 0.f;
-	float pdf = 0.f;
-	int lobes[4];
-	int n = LobeList(*b.mat, skipSpecular, lobes);
-	for (int i = 0; i < n; i++) pdf += Lobe_Pdf(*b.mat, lobes[i], wo, wi);
-	return n > 0 ? pdf / n : 0.f;
-}
-// *pdf is written only where upstream writes it (callers pre-set it like upstream's locals).
-__device__ __noinline__ float3 BSDF_Sample_f(const DBSDF& b, float3 woW, float3* wiW, float2 u, float* pdf,
-		bool skipSpecular, bool* sampledSpecular) {
-	int lobes[4];
-	int matching = LobeList(*b.mat, skipSpecular, lobes);
-	if (matching == 0) { *pdf = 0; return f3(0.f); }
-	int comp = min((int)floorf(u.x * matching), matching - 1);
-	int lobe = lobes[comp];
-	float2 uR = make_float2(smin(u.x * matching - comp, AGPT_ONE_MINUS_EPS), u.y);
-	float3 wi = f3(0.f), wo = WorldToLocal(b, woW);
-	if (wo.z == 0) return f3(0.f);
-	*pdf = 0;
-	bool specular = lobe == AGPT_LOBE_SPECULAR;
-	if (sampledSpecular) *sampledSpecular = specular;
-	float3 f = f3(0.f);
-	const agpt_material& m = *b.mat;
-	if (specular) {
-		wi = f3(-wo.x, -wo.y, wo.z);
-		*pdf = 1;
-		f = f3(1.f) * f3(m.mirror_r) / AbsCosTheta(wi);       // FresnelNoOp (microfacet.h:230-233)
-	}
-	else if (lobe == AGPT_LOBE_MICROFACET) {
-		// MicrofacetReflection::Sample_f (reflection.h:55-66): early returns leave *pdf = 0
-		float3 wh = TR_Sample_wh(m.alpha_x, m.alpha_y, wo, uR);
-		if (!(dot(wo, wh) < 0)) {
-			wi = Reflect(wo, wh);
-			if (SameHemisphere(wo, wi)) *pdf = TR_Pdf(m.alpha_x, m.alpha_y, wo, wh) / (4 * dot(wo, wh));
-		}
-	}
-	else {
-		// BxDF::Sample_f cosine sampling (reflection.h:8-15)
-		wi = CosineSampleHemisphere(uR);
-		if (wo.z < 0) wi.z *= -1;
-		*pdf = Cosine_Pdf(wo, wi);
-	}
-	if (*pdf == 0) return f3(0.f);
-	*wiW = LocalToWorld(b, wi);
-	if (!specular && matching > 1)
-		for (int i = 0; i < matching; i++)
-			if (lobes[i] != lobe) *pdf += Lobe_Pdf(m, lobes[i], wo, wi);
-	if (matching > 1) *pdf /= matching;
-	if (!specular) {
-		bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
-		f = f3(0.f);
-		for (int i = 0; i < matching; i++)
-			if (reflect) f += Lobe_f(m, lobes[i], wo, wi);
-	}
-	return f;
-}
 
 // ---------------------------------------------------------------------------------------
 // SurfaceInteraction (intersectable.h:63-115) rebuilt once for the closest hit
@@ -488,8 +369,8 @@ __device__ __forceinline__ float PowerHeuristic(int nf, float fPdf, int ng, floa
 // depend on wo only (local wo, Schlick weight, G1(wo)) are computed once per vertex and ONE
 // out-of-line evaluator returns, for a direction, the summed lobe values and the two distinct
 // lobe pdfs.  Every value is produced by the same operations in the same order as the
-// per-function restatement above (which the probe kernels keep testing against the reference),
-// so results stay bit-identical.
+// reference's per-function code (reflection.h:114-188); the probe kernel runs exactly these
+// functions against golden vectors of the reference's BSDF::f / Pdf / Sample_f.
 // ---------------------------------------------------------------------------------------
 struct VertexBsdf {
 	DBSDF b;
@@ -548,6 +429,19 @@ __device__ __noinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEval&
 		f += fm;
 	}
 	out.f = f;
+}
+
+// BSDF::f and BSDF::Pdf of a given world direction from one EvalLobes result (reflection.h:114-123,
+// 174-188; specular lobes contribute nothing to either).  The caller checks v.woOk.
+__device__ __forceinline__ float3 FinishEval(const VertexBsdf& v, const LobeEval& e, float3 wiW, float* pdfOut) {
+	const agpt_material& m = *v.b.mat;
+	bool reflect = dot(wiW, v.b.ng) * dot(v.woW, v.b.ng) > 0;
+	float p = 0.f;
+	if (m.lobes & AGPT_LOBE_DIFFUSE) p += e.pdfCos;
+	if (m.lobes & AGPT_LOBE_RETRO) p += e.pdfCos;
+	if (m.lobes & AGPT_LOBE_MICROFACET) p += e.pdfMicro;
+	*pdfOut = v.nLobes > 0 ? p / v.nLobes : 0.f;
+	return reflect ? e.f : f3(0.f);
 }
 
 struct DirSample {

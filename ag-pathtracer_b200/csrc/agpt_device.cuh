@@ -21,6 +21,19 @@
 #define AGPT_EPSILON 0.0001f
 #define AGPT_ONE_MINUS_EPS 0x1.fffffep-1f
 
+// -DAGPT_DEBUG build (make debug -> libagpt_debug.so): in-kernel checks on stack depth, node / triangle
+// indices and queue slots.  A failed check records its code and value in g_agptDebug (no trap: the
+// context stays usable) and agpt_debug_status() reports it.  compute-sanitizer is closed on the GPU
+// pool this was developed on, so the small GPU tests are run once per round against this build.
+enum { AGPT_DBG_STACK = 1, AGPT_DBG_NODE = 2, AGPT_DBG_TRI = 3, AGPT_DBG_QUEUE = 4, AGPT_DBG_PATH = 5, AGPT_DBG_PRIM = 6, AGPT_DBG_MATERIAL = 7 };
+#ifdef AGPT_DEBUG
+__device__ unsigned long long g_agptDebug[4];     // [0] failures, [1] first code, [2] first value, [3] checks executed
+#define AGPT_CHECK(cond, code, value) do { atomicAdd(&g_agptDebug[3], 1ull); if (!(cond)) { \
+	if (atomicAdd(&g_agptDebug[0], 1ull) == 0ull) { g_agptDebug[1] = (unsigned long long)(code); g_agptDebug[2] = (unsigned long long)(long long)(value); } } } while (0)
+#else
+#define AGPT_CHECK(cond, code, value) ((void)0)
+#endif
+
 struct DMesh {
 	const float4* nodes;     // 2 x float4 per BVHNode; nullptr for a plain TriangleMesh
 	const float4* tris;      // 3 x float4 per triangle, leaf order; tris[3j].w != 0 marks a triangle upstream rejects as degenerate
@@ -235,6 +248,83 @@ __device__ __noinline__ float ratan2(float y, float x) {
 	case 2: return pi - (z - pi_lo);
 	default: return (z - pi_lo) - pi;
 	}
+}
+
+// powf with the oracle's bits, for Accumulator::CopyToSurface's gamma (common.h:41-44: pow(c, 1/2.2f)
+// on floats = powf).  glibc 2.39's powf is the ARM optimized-routines algorithm
+// (sysdeps/ieee754/flt-32/e_powf.c, e_powf_log2_data.c, e_exp2f_data.c): log2(x) from a 16-entry
+// table + degree-5 polynomial, exp2 from a 32-entry table + cubic, all in double.  On x86-64 hosts
+// with FMA, glibc dispatches to the same source compiled with -mfma (__powf_fma), in which every
+// a*b+c below is one fused operation; the explicit fma() calls restate that build (--fmad=false
+// leaves explicit fma alone).  Checked on the host against libm for ALL 2,139,095,041 non-negative
+// float bit patterns with y = 1/2.2f: 0 mismatches.  Only what this path needs: y finite, > 0 and
+// not an integer (the special cases of e_powf.c:155-196 for such y).
+__device__ __noinline__ float rpowf(float x, float y) {
+	const double T[16][2] = {
+		{ 0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2 }, { 0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2 },
+		{ 0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2 }, { 0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2 },
+		{ 0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2 }, { 0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3 },
+		{ 0x1.1bb4a4a1a343fp+0, -0x1.2f9e393af3c9fp-3 }, { 0x1.12358f08ae5bap+0, -0x1.960cbbf788d5cp-4 },
+		{ 0x1.0953f419900a7p+0, -0x1.a6f9db6475fcep-5 }, { 0x1.0000000000000p+0, 0x0.0p+0 },
+		{ 0x1.e608cfd9a47acp-1, 0x1.338ca9f24f53dp-4 }, { 0x1.ca4b31f026aa0p-1, 0x1.476a9543891bap-3 },
+		{ 0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3 }, { 0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2 },
+		{ 0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2 }, { 0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2 } };
+	const double A0 = 0x1.27616c9496e0bp-2, A1 = -0x1.71969a075c67ap-2, A2 = 0x1.ec70a6ca7baddp-2, A3 = -0x1.7154748bef6c8p-1, A4 = 0x1.71547652ab82bp+0;
+	const unsigned long long E[32] = {
+		0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull, 0x3fef72b83c7d517bull, 0x3fef54873168b9aaull,
+		0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull, 0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+		0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull, 0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull,
+		0x3feea11473eb0187ull, 0x3feea589994cce13ull, 0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+		0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull, 0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full,
+		0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull };
+	const double C0 = 0x1.c6af84b912394p-5, C1 = 0x1.ebfce50fac4f3p-3, C2 = 0x1.62e42ff0c52d6p-1, SHIFT = 0x1.8p+47;
+	uint32_t ix = __float_as_uint(x);
+	if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+		// x is zero, subnormal, negative, inf or nan
+		if (2u * ix == 0u) return 0.0f;                                   // (+-0)^y = +0 for y > 0 not an odd integer
+		if ((ix & 0x7fffffffu) > 0x7f800000u) return x + y;               // nan
+		if (ix == 0x7f800000u || ix == 0xff800000u) return __uint_as_float(0x7f800000u);   // (+-inf)^y = +inf
+		if (ix & 0x80000000u) return __uint_as_float(0xffc00000u);       // negative finite base, non-integer y: invalid -> the x86 default nan of (x-x)/(x-x)
+		ix = __float_as_uint(x * 0x1p23f);                                // subnormal: normalise
+		ix &= 0x7fffffffu;
+		ix -= 23u << 23;
+	}
+	// log2_inline (e_powf.c:44-77)
+	uint32_t tmp = ix - 0x3f330000u;
+	int i = (int)((tmp >> (23 - 4)) % 16u);
+	uint32_t top = tmp & 0xff800000u;
+	uint32_t iz = ix - top;
+	int k = (int)top >> 23;
+	double invc = T[i][0], logc = T[i][1];
+	double z = (double)__uint_as_float(iz);
+	double r = fma(z, invc, -1.0);
+	double y0 = logc + (double)k;
+	double r2 = r * r;
+	double yy = fma(A0, r, A1);
+	double p = fma(A2, r, A3);
+	double r4 = r2 * r2;
+	double q = fma(A4, r, y0);
+	q = fma(p, r2, q);
+	yy = fma(yy, r4, q);
+	double ylogx = (double)y * yy;
+	if (((unsigned long long)__double_as_longlong(ylogx) >> 47 & 0xffffull) >= ((unsigned long long)__double_as_longlong(126.0) >> 47)) {
+		if (ylogx > 0x1.fffffffd1d571p+6) return __uint_as_float(0x7f800000u);      // overflow
+		if (ylogx <= -150.0) return 0.0f;                                            // underflow
+	}
+	// exp2_inline (e_powf.c:96-127)
+	double kd = ylogx + SHIFT;
+	unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+	kd -= SHIFT;
+	double rr = ylogx - kd;
+	unsigned long long t = E[ki % 32ull];
+	t += ki << (52 - 5);
+	double s = __longlong_as_double((long long)t);
+	double zz = fma(C0, rr, C1);
+	double rr2 = rr * rr;
+	double y2 = fma(C2, rr, 1.0);
+	y2 = fma(zz, rr2, y2);
+	y2 = y2 * s;
+	return (float)y2;
 }
 
 // common.h:145-151

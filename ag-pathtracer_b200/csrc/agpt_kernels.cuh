@@ -22,26 +22,10 @@
 #define PF_NO_CONTINUE   8u     // path ended at the previous vertex; only its NEE is left to fold in
 #define PF_BOUNCE_SHIFT  8
 
-// Path state streams through the chip once per kernel (>= 100 MB per wave, far more than any
-// reuse distance the caches could cover), while the BVH tables are re-read by every ray.  State
-// accesses therefore carry the cache-streaming hint (ld/st.global.cs = evict-first), so they do
-// not push nodes and triangles out of L2 between trace launches.
-#ifndef AGPT_STREAM_STATE
-#define AGPT_STREAM_STATE 0
-#endif
+// Path state is plain SoA in HBM.  (Cache-streaming hints -- ld/st.global.cs -- on these accesses,
+// to keep the state from pushing BVH nodes out of L2, measured +-0.5 %: not kept.)
 template <typename T>
-struct StateRef {
-	T* p;
-	__device__ __forceinline__ operator T() const { return AGPT_STREAM_STATE ? __ldcs(p) : *p; }
-	__device__ __forceinline__ void operator=(const T& v) const { if (AGPT_STREAM_STATE) __stcs(p, v); else *p = v; }
-};
-template <typename T>
-struct StateArray {
-	T* p;
-	__host__ __device__ __forceinline__ StateArray& operator=(T* q) { p = q; return *this; }
-	__host__ __device__ __forceinline__ operator T*() const { return p; }
-	__device__ __forceinline__ StateRef<T> operator[](int i) const { return StateRef<T>{ p + i }; }
-};
+using StateArray = T*;
 
 struct PathState {
 	StateArray<float4> rayO;        // O.xyz, tmax
@@ -62,6 +46,7 @@ struct PathState {
 	StateArray<int> shadowOccluded;
 	StateArray<int> misPrim;        // primitive hit by the MIS ray, -1 = none
 	StateArray<float4> Lout;        // finished radiance per path slot
+	int slots;                      // allocated path slots (debug checks)
 };
 
 #ifndef AGPT_STEEP_BIT
@@ -220,6 +205,7 @@ struct GenParams {
 	const int* ss;
 	const float* rays7;    // optional explicit rays (li_rays); O, D, tmax
 	const uint32_t* seeds;
+	int raysFinal;         // rays7 directions are unit length already (a host Ray object): use as given
 	int tiled;             // whole-film mode of agpt_render: slot = tile-order pixel slot * samples + sample (else sample-major rows)
 	int samples;           // samples per pixel in this batch (tiled mode)
 };
@@ -251,7 +237,8 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 	uint32_t rng;
 	if (g.rays7) {
 		const float* r = g.rays7 + 7 * (size_t)i;
-		ray = MakeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]), r[6]);
+		if (g.raysFinal) { ray.O = f3(r[0], r[1], r[2]); ray.D = f3(r[3], r[4], r[5]); ray.t = r[6]; }
+		else ray = MakeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]), r[6]);
 		rng = g.seeds[i] ? g.seeds[i] : 1u;
 	}
 	else {
@@ -297,6 +284,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 	bool lane = i < count;
 	if (!lane) e = 0;
 	int path = e >> 1, kind = e & 1;
+	AGPT_CHECK(path >= 0 && path < ps.slots, AGPT_DBG_PATH, path);
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) {
 		o = kind ? ps.misO[path] : ps.rayO[path];
@@ -324,6 +312,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 	const int count = *countPtr;
 	bool lane = i < count;
 	if (!lane) path = 0;
+	AGPT_CHECK(path >= 0 && path < ps.slots, AGPT_DBG_PATH, path);
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = ps.shO[path]; d = ps.shD[path]; }
 	HitRecord hit;
@@ -363,12 +352,6 @@ struct ShadeParams {
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
 };
 
-__device__ __forceinline__ float3 LightLeInfinite(const DScene& sc) {
-	// for (light : scene.lights) if (light->IsInfinite()) L += beta * light->Le(ray)  (integrator.h:144-145)
-	// handled by the caller per light to keep the add order
-	return f3(0.f);
-}
-
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
 //
 // Shade is two kernels.  Most entries of the active list need almost no work: their path left
@@ -389,6 +372,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 	int path = active[i];              // unconditional (allocation slack), overlaps with the count load
 	const bool valid = i < *activeCount;
 	if (!valid) path = 0;
+	AGPT_CHECK(path >= 0 && path < ps.slots, AGPT_DBG_PATH, path);
 	bool survive = false;
 	if (valid) {
 		// (loading the NEE terms unconditionally, to save the dependent round trip, measured slower:
@@ -424,6 +408,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 		if (!(flags & PF_NO_CONTINUE)) {
 			// (2) the new vertex: did the ray hit, and is there emission to add (integrator.h:139-147)
 			int hitPrim = __float_as_int(h.w);
+			AGPT_CHECK(hitPrim < sc.n_prims, AGPT_DBG_PRIM, hitPrim);
 			bool found = hitPrim >= 0;
 			int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
 			if (bounces == 0 || (flags & PF_SPECULAR)) {
@@ -481,15 +466,6 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 #define AGPT_SHADE_MIN_BLOCKS 1
 #endif
 
-#ifndef AGPT_SHADE_PHASE_SYNC
-#define AGPT_SHADE_PHASE_SYNC 0      // block barrier before each phase (every thread of a block reaches them)
-#endif
-#if AGPT_SHADE_PHASE_SYNC
-#define SHADE_PHASE_BARRIER() __syncthreads()
-#else
-#define SHADE_PHASE_BARRIER() ((void)0)
-#endif
-
 template <bool ENV>
 __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
@@ -506,6 +482,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 		uint32_t rng = 0;
 		if (valid) {
 			path = survivors[i];
+			AGPT_CHECK(path >= 0 && path < ps.slots, AGPT_DBG_PATH, path);
 			flags = ps.flags[path];
 			o4 = ps.rayO[path]; d4 = ps.rayD[path]; h = ps.hitA[path];
 			float4 b4 = ps.beta[path];
@@ -521,10 +498,11 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 		int bounces = (int)(flags >> PF_BOUNCE_SHIFT);
 		DSurface si;
 		si.p = f3(0.f); si.n = f3(0.f); si.sn = f3(0.f); si.sdpdu = f3(0.f);
-		const agpt_material* mat = sc.mats;
+		const agpt_material* mat = sc.mats;      // (never null: agpt keeps one dummy record resident when the scene has no materials)
 
 		// the surface at the hit (a survivor has one); null materials pass straight through
 		if (valid) {
+			AGPT_CHECK(__float_as_int(h.w) >= 0 && __float_as_int(h.w) < sc.n_prims, AGPT_DBG_PRIM, __float_as_int(h.w));
 			agpt_prim prim = sc.prims[__float_as_int(h.w)];
 			// SurfaceInteraction of the closest hit
 			if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
@@ -542,7 +520,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			else { full = true; mat = sc.mats + prim.material; }
 		}
 
-		SHADE_PHASE_BARRIER();
 		// ================= phase B: BSDF frame, random numbers, light sample =================
 		const float3 wo = -D;
 		VertexBsdf vb;
@@ -614,7 +591,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 		}
 		const bool evalLight = doNee && lightPdf > 0 && !IsBlack(Li);
 
-		SHADE_PHASE_BARRIER();
 		// ================= phase C: sample the MIS and the continuation directions =================
 		DirSample smp[2];
 	#pragma unroll 1
@@ -624,7 +600,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			else { smp[k].ok = false; smp[k].lobe = 0; smp[k].matching = 0; smp[k].pdf = 0; smp[k].wi = f3(0.f); smp[k].fSpec = f3(0.f); }
 		}
 
-		SHADE_PHASE_BARRIER();
 		// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
 		float3 fDir[3];
 		float pdfDir[3];
@@ -639,16 +614,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
 			if (need) EvalLobes(vb, wiLoc, ev);
 			if (k == 0) {
-				if (need) {
-					// BSDF::f and BSDF::Pdf at the light direction (reflection.h:114-123,174-188)
-					bool reflect = dot(wiL, vb.b.ng) * dot(wo, vb.b.ng) > 0;
-					fDir[0] = reflect ? ev.f : f3(0.f);
-					float p = 0.f;
-					if (mat->lobes & AGPT_LOBE_DIFFUSE) p += ev.pdfCos;
-					if (mat->lobes & AGPT_LOBE_RETRO) p += ev.pdfCos;
-					if (mat->lobes & AGPT_LOBE_MICROFACET) p += ev.pdfMicro;
-					pdfDir[0] = vb.nLobes > 0 ? p / vb.nLobes : 0.f;
-				}
+				if (need) fDir[0] = FinishEval(vb, ev, wiL, &pdfDir[0]);     // BSDF::f and BSDF::Pdf at the light direction
 				wiWorld[0] = wiL;
 			}
 			else if (full && sampled) {
@@ -657,7 +623,6 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			}
 			}
 
-		SHADE_PHASE_BARRIER();
 		// ================= phase E: EstimateDirect terms, throughput, next rays =================
 		if (full) {
 			// (3) EstimateDirect (integrator.h:38-93)
@@ -797,6 +762,8 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			if (mTc) atomicAdd(&blockStats[5], __popc(mTc));
 		}
 		__syncthreads();
+		AGPT_CHECK(queueBase[0] + warpCount[warp][1] + __popc(mM) <= 2 * ps.slots && queueBase[1] + warpCount[warp][2] + __popc(mS) <= ps.slots &&
+			queueBase[2] + warpCount[warp][3] + __popc(mA) <= ps.slots, AGPT_DBG_QUEUE, queueBase[0]);
 		if (emitExtend) { int slot = queueBase[0] + warpCount[warp][0] + __popc(mE & below); qout.closest[slot] = path * 2; qout.keys[slot] = (unsigned short)keyExtend; }
 		if (emitMis) { int slot = queueBase[0] + warpCount[warp][1] + __popc(mM & below); qout.closest[slot] = path * 2 + 1; qout.keys[slot] = (unsigned short)keyMis; }
 		if (emitShadow) { int slot = queueBase[1] + warpCount[warp][2] + __popc(mS & below); qout.shadow[slot] = path; qout.shadowKeys[slot] = (unsigned short)keyShadow; }
@@ -832,16 +799,20 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ L
 }
 
 // ---- resolve: Accumulator::CopyToSurface (myapp.h:34-41) + lin2rgb / rgb2uint (common.h:41-51)
+// One pixel of CopyToSurface: pixels / (float)samples -> lin2rgb -> rgb2uint.  powf is glibc's
+// (rpowf), so the packed bytes equal the reference's for every float input, not just "within 1 LSB".
+// rgb2uint's clamp(clr.x, 0.0, 0.999) resolves to the template's float overload (precomp.h:678):
+// fmaxf(0.f, fminf(f, 0.999f)) with the a<b?a:b / a>b?a:b semantics (a NaN channel comes out 255).
+__device__ __forceinline__ uint32_t ResolvePixel(float4 a, float samples) {
+	const float e = 1 / 2.2f;
+	float3 c = f3(rpowf(a.x / samples, e), rpowf(a.y / samples, e), rpowf(a.z / samples, e));
+	int r = (int)(256 * rclamp(c.x, 0.0f, 0.999f)), g = (int)(256 * rclamp(c.y, 0.0f, 0.999f)), b = (int)(256 * rclamp(c.z, 0.0f, 0.999f));
+	return (uint32_t)((r << 16) + (g << 8) + b);
+}
 __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accum, uint32_t* out, int n, float samples) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	float4 a = accum[i];
-	float e = 1 / 2.2f;
-	float3 c = f3(powf(a.x / samples, e), powf(a.y / samples, e), powf(a.z / samples, e));
-	// rgb2uint clamps in double: clamp(clr.x, 0.0, 0.999) (common.h:47)
-	auto ch = [](float v) { double d = (double)v; d = d < 0.999 ? d : 0.999; d = 0.0 > d ? 0.0 : d; return (int)(256 * d); };
-	int r = ch(c.x), g = ch(c.y), b = ch(c.z);
-	out[i] = (uint32_t)((r << 16) + (g << 8) + b);
+	out[i] = ResolvePixel(accum[i], samples);
 }
 
 // ---- upload-time pass: flag triangles upstream would reject as degenerate (trianglemesh.cpp:71-77)

@@ -22,7 +22,10 @@
 #ifndef AGPT_TRACE_MIN_BLOCKS
 #define AGPT_TRACE_MIN_BLOCKS 16  // <= 64 registers: 1024 threads per SM (measured: 71 registers is 7 % slower)
 #endif
-#define AGPT_STACK_LOCAL 40     // overflow entries in local memory (SAH trees here are <= ~30 deep)
+#ifndef AGPT_STACK_LOCAL
+#define AGPT_STACK_LOCAL 104    // overflow entries in local memory: 128 levels in all.  SAH trees over real meshes are <= ~30
+                                // deep (the shared-memory part); agpt_upload_meshes refuses trees deeper than the stack.
+#endif
 #ifndef AGPT_TRACE_THREADS
 #define AGPT_TRACE_THREADS 64     // small blocks retire early when their rays are short (128: +1 %, 256: +8 %, 512: +25 % trace time)
 #endif
@@ -145,7 +148,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
-						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
 							found = true;
 							if (ANY) break;
 							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
@@ -198,6 +201,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 					unsigned el = EncodeNode((int)cur, l.first, l.count), er = EncodeNode((int)cur + 1, r.first, r.count);
 					if (hl && hr) {
 						unsigned farE = swapKids ? el : er;
+						AGPT_CHECK(sp < AGPT_STACK_SMEM + AGPT_STACK_LOCAL, AGPT_DBG_STACK, sp);
 						if (sp < AGPT_STACK_SMEM) stack[sp * stackStride] = farE; else local[sp - AGPT_STACK_SMEM] = farE;
 						sp++;
 						cur = swapKids ? er : el;
@@ -216,7 +220,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
-						if (a.w == 0.f && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
 							found = true;
 							if (ANY) break;
 							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
@@ -244,24 +248,9 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 
 // Scene::Intersect (ANY=false) / Scene::IntersectP (ANY=true): primitives in list order.
 // Every lane of the warp must call (lane=false for threads without a ray).
-//
-// AGPT_ANALYTIC_FIRST=1 (off: measured slower) reorders the closest-hit tests without changing
-// the result.  Upstream tests the primitives in list order with a shrinking ray.t, so a mesh early
-// in the list (a backdrop, a room) is walked with ray.t = infinity although a plane or sphere
-// later in the list ends the ray long before.  With the option the spheres and planes are tested
-// first, in their list order, and the meshes afterwards, in theirs, with ray.t starting one ulp
-// above the analytic hit -- so a triangle at exactly that distance is still found -- and the two
-// candidates are merged by the rule the in-order scan implies for equal t: a sphere wins
-// (Sphere::Intersect accepts root <= ray.t and so replaces whatever came before; a triangle or
-// plane needs t < ray.t and so never replaces it), otherwise the lower list index wins.  Which
-// root a sphere reports does not depend on ray.t (only whether it is accepted), and a mesh's own
-// winner does not depend on the ray.t it is entered with as long as that is above its hit, so the
-// result is upstream's (the GPU tests pass with it).  It costs a second pass over the primitive
-// list and registers, and the tighter ray.t prunes little: closest-hit +13 % on cfg 3, +10 % in
-// the closed room.
-#ifndef AGPT_ANALYTIC_FIRST
-#define AGPT_ANALYTIC_FIRST 0
-#endif
+// (Testing the spheres and planes first and the meshes afterwards, with an exact tie-aware merge,
+// was measured: closest-hit +13 % on cfg 3, +10 % in the closed room -- a second pass over the
+// primitive list for little extra pruning.  Not kept; numbers in DESIGN.md.)
 template <bool ANY, bool COUNT, bool FAST>
 __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D, float rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
@@ -271,84 +260,61 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
 	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
 		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
-	const bool twoPass = !ANY && !COUNT && AGPT_ANALYTIC_FIRST;
-	const float rayT0 = rayT;
-	HitRecord hitA;                      // two-pass: the analytic candidate while the meshes are walked
-	hitA.prim = -1; hitA.slot = -1; hitA.t = 0.f; hitA.b1 = 0.f; hitA.b2 = 0.f;
-	bool foundA = false, sphereA = false;
-	bool lastSphere = false;             // the hit in `hit` is on a sphere
-	for (int pass = 0; pass < (twoPass ? 2 : 1); pass++) {
-		if (twoPass && pass == 1) {
-			hitA = hit; foundA = found; sphereA = lastSphere;
-			hit.prim = -1; hit.slot = -1;
-			found = false;
-			rayT = foundA ? fminf(rayT0, nextafterf(hitA.t, 3.0e38f)) : rayT0;
-		}
-		int p = 0;
-		while (p < sc.n_prims) {
-			agpt_prim prim = sc.prims[p];
-			bool test = lane && !(ANY && found);
-			if (ANY && !__any_sync(0xffffffffu, test)) break;     // warp-uniform early out of IntersectP
-			if (prim.type == AGPT_PRIM_SPHERE) {
-				// a run of spheres with consecutive payloads: straight through the sphere table
-				const int len = sc.sphereRun[p];
-				if (twoPass && pass == 1) { p += len; continue; }
-				const agpt_sphere* sp = sc.spheres + prim.payload;
-				if (len >= AGPT_RUN_CULL_MIN) {
-					// Exact cull of the whole run: its spheres sit in a box grown by 5 % of the smallest
-					// radius.  A ray that certainly misses that box passes every sphere at more than
-					// r + 0.05 r, and as long as the origin is near enough (runBox.w: |oc|^2 below
-					// 2e4 r^2) the rounding of Sphere::Intersect's discriminant, < 1.3e-6 |oc|^2, is far
-					// too small to turn such a miss into a hit.  If no lane of the warp can hit the
-					// box the run is skipped (analytic_tests counts the records really read).
-					const float4 b0 = __ldg(sc.sphereRunBox + 3 * p), b1 = __ldg(sc.sphereRunBox + 3 * p + 1), b2 = __ldg(sc.sphereRunBox + 3 * p + 2);
-					bool maybe = test;
-					if (test && filterOk) {
-						float3 oc = O - f3(b2.x, b2.y, b2.z);
-						if (sqrLength(oc) < b2.w) {
-							float tn, tx;
-							SlabApprox(f3(b0.x, b0.y, b0.z), f3(b0.w, b1.x, b1.y), O, rD, rayT, tn, tx);
-							maybe = SlabDecision(tn, tx) != 0;
-						}
-					}
-					if (COUNT && test) cnt.analytic_tests++;          // the box record counts as one analytic record read
-					if (!__any_sync(0xffffffffu, maybe)) { p += len; continue; }
-				}
-				for (int j = 0; j < len; j++) {
-					bool tj = test && !(ANY && found);
-					if (COUNT && tj) cnt.analytic_tests++;
-					float t;
-					if (tj && SphereTest(sp[j], O, D, rayT, t)) {
-						if (!ANY) { rayT = t; hit.t = t; hit.prim = p + j; hit.slot = -1; lastSphere = true; }
-						found = true;
+	int p = 0;
+	while (p < sc.n_prims) {
+		agpt_prim prim = sc.prims[p];
+		bool test = lane && !(ANY && found);
+		if (ANY && !__any_sync(0xffffffffu, test)) break;     // warp-uniform early out of IntersectP
+		if (prim.type == AGPT_PRIM_SPHERE) {
+			// a run of spheres with consecutive payloads: straight through the sphere table
+			const int len = sc.sphereRun[p];
+			const agpt_sphere* sp = sc.spheres + prim.payload;
+			if (len >= AGPT_RUN_CULL_MIN) {
+				// Exact cull of the whole run: its spheres sit in a box grown by 5 % of the smallest
+				// radius.  A ray that certainly misses that box passes every sphere at more than
+				// r + 0.05 r, and as long as the origin is near enough (runBox.w: |oc|^2 below
+				// 2e4 r^2) the rounding of Sphere::Intersect's discriminant, < 1.3e-6 |oc|^2, is far
+				// too small to turn such a miss into a hit.  If no lane of the warp can hit the
+				// box the run is skipped (analytic_tests counts the records really read).
+				const float4 b0 = __ldg(sc.sphereRunBox + 3 * p), b1 = __ldg(sc.sphereRunBox + 3 * p + 1), b2 = __ldg(sc.sphereRunBox + 3 * p + 2);
+				bool maybe = test;
+				if (test && filterOk) {
+					float3 oc = O - f3(b2.x, b2.y, b2.z);
+					if (sqrLength(oc) < b2.w) {
+						float tn, tx;
+						SlabApprox(f3(b0.x, b0.y, b0.z), f3(b0.w, b1.x, b1.y), O, rD, rayT, tn, tx);
+						maybe = SlabDecision(tn, tx) != 0;
 					}
 				}
-				p += len;
+				if (COUNT && test) cnt.analytic_tests++;          // the box record counts as one analytic record read
+				if (!__any_sync(0xffffffffu, maybe)) { p += len; continue; }
 			}
-			else if (prim.type == AGPT_PRIM_PLANE) {
-				if (twoPass && pass == 1) { p++; continue; }
-				if (COUNT && test) cnt.analytic_tests++;
+			for (int j = 0; j < len; j++) {
+				bool tj = test && !(ANY && found);
+				if (COUNT && tj) cnt.analytic_tests++;
 				float t;
-				if (test && PlaneTest(sc.planes[prim.payload], O, D, rayT, t)) {
-					if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; lastSphere = false; }
+				if (tj && SphereTest(sp[j], O, D, rayT, t)) {
+					if (!ANY) { rayT = t; hit.t = t; hit.prim = p + j; hit.slot = -1; }
 					found = true;
 				}
-				p++;
 			}
-			else {
-				int q = p + 1;                                     // run of consecutive mesh primitives (<= 32 per call)
-				while (q < sc.n_prims && q < p + 32 && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
-				if (!(twoPass && pass == 0)) {
-					if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rD, filterOk, rayT, hit, stack, stackStride, cnt, test)) { found = true; lastSphere = false; }
-				}
-				p = q;
-			}
+			p += len;
 		}
-	}
-	if (twoPass) {
-		// merge the mesh candidate (in hit / found) with the analytic one
-		bool takeA = foundA && (!found || hitA.t < hit.t || (hitA.t == hit.t && (sphereA || hitA.prim < hit.prim)));
-		if (takeA) { hit = hitA; found = true; }
+		else if (prim.type == AGPT_PRIM_PLANE) {
+			if (COUNT && test) cnt.analytic_tests++;
+			float t;
+			if (test && PlaneTest(sc.planes[prim.payload], O, D, rayT, t)) {
+				if (!ANY) { rayT = t; hit.t = t; hit.prim = p; hit.slot = -1; }
+				found = true;
+			}
+			p++;
+		}
+		else {
+			int q = p + 1;                                     // run of consecutive mesh primitives (<= 32 per call)
+			while (q < sc.n_prims && q < p + 32 && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
+			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rD, filterOk, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			p = q;
+		}
 	}
 	return found;
 }

@@ -29,7 +29,7 @@ public:
 	inline void IncrementSampleCount() { samples++; }
 	inline int NumSamples() const { return samples; }
 	inline void Clear() {
-		memset(pixels, 0, (size_t)width * height * sizeof(float3));
+		memset((void*)pixels, 0, (size_t)width * height * sizeof(float3));
 		samples = 0;
 	}
 	inline float2 PixelToFilm(const float2& p) const { return float2(p.x / width, p.y / height); }

@@ -30,8 +30,9 @@ public:
 	CudaPathTracer(const CudaPathTracer&) = delete;
 	CudaPathTracer& operator=(const CudaPathTracer&) = delete;
 
-	// Upload (or re-upload) the flattened scene.  Called implicitly by Render/Li when the
-	// Scene object changes; call explicitly after editing a scene in place.
+	// Upload (or re-upload) the flattened scene.  Called implicitly by Render/Li whenever the
+	// scene's fingerprint differs from the resident one (another Scene object, or primitives /
+	// lights added since).
 	void Upload(const Scene& scene) const {
 		auto flat = scene.Flatten();
 		Check(agpt_upload_meshes(ctx, flat->meshes.data(), (int)flat->meshes.size()));
@@ -41,14 +42,14 @@ public:
 		Check(agpt_upload_lights(ctx, flat->lights.data(), (int)flat->lights.size()));
 		Check(agpt_upload_envmap(ctx, flat->envmap.width > 0 ? &flat->envmap : nullptr));
 		Check(agpt_upload_primitives(ctx, flat->prims.data(), (int)flat->prims.size()));
-		uploaded = &scene;
+		uploaded = scene.Fingerprint();
 	}
 
 	// numSamples Tick bodies: samples firstSample .. firstSample+numSamples-1 of every pixel,
 	// added to `acc` (which keeps its earlier contents, like successive Ticks do).
 	void Render(const Scene& scene, const Camera& camera, Accumulator& acc, int firstSample, int numSamples,
 			int depth = 0, uint32_t flags = 0) const {
-		if (uploaded != &scene) Upload(scene);
+		if (uploaded != scene.Fingerprint()) Upload(scene);
 		agpt_camera cam = camera.Export();
 		Check(agpt_set_camera(ctx, &cam));
 		Check(agpt_set_film(ctx, acc.width, acc.height));
@@ -71,17 +72,17 @@ protected:
 	}
 	int MaxDepth;
 	agpt_ctx* ctx = nullptr;
-	mutable const Scene* uploaded = nullptr;
+	mutable uint64_t uploaded = 0;     // Scene::Fingerprint() of the resident tables (0: none)
 	mutable unsigned liCalls = 0;
 };
 
 // (defined here so that the mirror stays header-only; libagpt.so is the only link dependency)
 inline float3 CudaPathTracer::Li(const Ray& ray, const Scene& scene, int depth) const {
-	if (uploaded != &scene) Upload(scene);
+	if (uploaded != scene.Fingerprint()) Upload(scene);
 	float r7[7] = { ray.O.x, ray.O.y, ray.O.z, ray.D.x, ray.D.y, ray.D.z, ray.t };
 	uint32_t seed = 0x12345678u + 0x9e3779b9u * liCalls++;   // upstream's global seed, advanced per call
 	float out[3] = { 0, 0, 0 };
-	Check(agpt_li_rays(ctx, 1, r7, &seed, MaxDepth, depth, out));
+	Check(agpt_li_rays(ctx, 1, r7, &seed, MaxDepth, depth, AGPT_FLAG_RAYS_FINAL, out));      // ray.D is final: the Ray ctor normalised it
 	return float3(out[0], out[1], out[2]);
 }
 

@@ -7,6 +7,7 @@
 // (a sphere accepts root == ray.t, triangles and planes reject t >= ray.t).
 #pragma once
 
+#include <atomic>
 #include <map>
 
 #include "precomp.h"
@@ -122,7 +123,24 @@ public:
 		return flat;
 	}
 
+	// What an uploaded copy of this scene is keyed on (CudaPathTracer): the object's serial number --
+	// a different Scene later constructed at the same address gets a new one -- mixed with the
+	// identities of its primitives and lights, so push_back / addAreaLight after an upload are seen.
+	// Shapes, materials and lights are immutable after construction upstream, so identity is content.
+	uint64_t Fingerprint() const {
+		uint64_t h = 0xcbf29ce484222325ull ^ serial;
+		auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x100000001b3ull; };
+		mix(primitives.size()); mix(lights.size());
+		for (auto& p : primitives) mix((uint64_t)(uintptr_t)p.get());
+		for (auto& l : lights) mix((uint64_t)(uintptr_t)l.get());
+		return h;
+	}
+
 	vector<shared_ptr<Intersectable>> primitives;
 	vector<shared_ptr<Light>> lights;
 	CameraDesc camera;
+
+private:
+	static uint64_t NextSerial() { static std::atomic<uint64_t> next(1); return next.fetch_add(1); }
+	uint64_t serial = NextSerial();
 };

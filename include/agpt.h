@@ -176,8 +176,10 @@ typedef struct agpt_stats {
 enum {
 	AGPT_FLAG_COUNTERS = 1u,      /* count node visits / box / triangle tests (slower kernels) */
 	AGPT_FLAG_TIMING = 2u,        /* bracket every kernel class with CUDA events (serialises) */
-	AGPT_FLAG_STRICT_BOXES = 4u   /* every slab test with the reference's six IEEE divisions; the default is the
+	AGPT_FLAG_STRICT_BOXES = 4u,  /* every slab test with the reference's six IEEE divisions; the default is the
 	                                 exact-filtered test (same decisions, divisions only inside a guard band) */
+	AGPT_FLAG_RAYS_FINAL = 8u     /* agpt_trace_rays / agpt_li_rays: directions are used as given -- the rays come from host
+	                                 Ray objects, whose constructor has normalised them already (camera.h:7) */
 };
 
 /* ---- lifecycle --------------------------------------------------------------------- */
@@ -215,7 +217,7 @@ int agpt_render(agpt_ctx* ctx, int first_sample, int num_samples, int sample_str
 int agpt_trace_primary(agpt_ctx* ctx, int sample, uint32_t flags, agpt_hit* out_host);
 
 /* Scene::Intersect (any_hit = 0) / Scene::IntersectP (any_hit != 0) for caller rays:
- * rays7 = O.xyz, D.xyz (normalised like the Ray ctor, camera.h:7), tmax. */
+ * rays7 = O.xyz, D.xyz (normalised on the device like the Ray ctor, camera.h:7, unless AGPT_FLAG_RAYS_FINAL), tmax. */
 int agpt_trace_rays(agpt_ctx* ctx, int64_t n, const float* rays7, int any_hit, uint32_t flags, agpt_hit* out_host);
 
 /* Radiance of single camera paths without accumulation (Integrator::Li for the debug
@@ -227,7 +229,7 @@ int agpt_li_pixels(agpt_ctx* ctx, int n, const int* xs, const int* ys, const int
  * in agpt_trace_rays, rng_states[i] = xorshift32 state the path starts from (the reference
  * draws from its one global generator instead). */
 int agpt_li_rays(agpt_ctx* ctx, int n, const float* rays7, const uint32_t* rng_states,
-		int max_depth, int rr_depth_arg, float* out_rgb);
+		int max_depth, int rr_depth_arg, uint32_t flags, float* out_rgb);
 
 /* ---- accumulator (Accumulator, myapp.h:8-68) ----------------------------------------- */
 
@@ -248,6 +250,10 @@ int agpt_host_free(void* p);
 
 int agpt_get_stats(agpt_ctx* ctx, agpt_stats* out);
 int agpt_reset_stats(agpt_ctx* ctx);
+/* Builds with -DAGPT_DEBUG (libagpt_debug.so) check stack depth, node / triangle / primitive indices and queue
+ * slots inside the kernels.  out4 = { failed checks, code of the first failure, its value, checks executed }
+ * since the library was loaded; a release build reports 0 checks executed. */
+int agpt_debug_status(agpt_ctx* ctx, uint64_t* out4);
 
 /* ---- per-function probes (differential tests against single reference functions) ----- */
 

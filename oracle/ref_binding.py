@@ -143,6 +143,14 @@ def ray_counts(reset=True):
     return dict(closest=out[0], any=out[1])
 
 
+def resolve(accum_rgba, samples):
+    """Accumulator::CopyToSurface arithmetic (the reference's own lin2rgb / rgb2uint) on a float4 buffer."""
+    a = np.ascontiguousarray(accum_rgba, np.float32).reshape(-1, 4)
+    out = np.zeros(len(a), np.uint32)
+    lib().agpt_ref_resolve(_fp(a), c_longlong(len(a)), c_int(samples), out.ctypes.data_as(POINTER(c_uint)))
+    return out.reshape(np.shape(accum_rgba)[:-1])
+
+
 def probe_bounds(boxes6, rays7):
     boxes6 = np.ascontiguousarray(boxes6, np.float32).reshape(-1, 6)
     rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)

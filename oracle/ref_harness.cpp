@@ -291,6 +291,17 @@ void agpt_ref_li_pixels(void* h, int W, int H, int n, const int* xs, const int* 
 	}
 }
 
+// Accumulator::CopyToSurface (myapp.h:34-41) on an accumulator-layout float4 buffer: the loop body
+// restated (Surface needs GLFW), its arithmetic -- float3 / float, lin2rgb, rgb2uint -- is the
+// reference's own (template/precomp.h:642, common.h:41-51), compiled from where it lies.
+void agpt_ref_resolve(const float* rgba, long long n, int samples, unsigned* out_rgb8) {
+	for (long long i = 0; i < n; i++) {
+		float3 px(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2]);
+		auto rgb = lin2rgb(px / (float)samples);
+		out_rgb8[i] = rgb2uint(rgb);
+	}
+}
+
 // ---- exports of built reference objects (for comparison with the host mirror) ----------
 
 // Camera: origin, lower_left_corner, horizontal, vertical, u, v (3 floats each) + lens_radius.
