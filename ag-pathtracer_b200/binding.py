@@ -35,6 +35,42 @@ class Material(ctypes.Structure):  # agpt_material
                 ("mirror_r", c_float * 3), ("alpha_y", c_float)]
 
 
+class BvhNode(ctypes.Structure):  # agpt_bvh_node
+    _fields_ = [("bmin", c_float * 3), ("bmax", c_float * 3), ("first", c_int32), ("count", c_int32)]
+
+
+class MeshDesc(ctypes.Structure):  # agpt_mesh_desc
+    _fields_ = [("nodes", c_void_p), ("n_nodes", c_int32), ("n_tris", c_int32), ("tri_verts", c_void_p), ("tri_ids", c_void_p),
+                ("tri_normals", c_void_p), ("tri_uvs", c_void_p)]
+
+
+PRIM_DTYPE = np.dtype([("type", np.int32), ("payload", np.int32), ("material", np.int32), ("area_light", np.int32)])        # agpt_prim
+SPHERE_DTYPE = np.dtype([("center", np.float32, 3), ("r", np.float32), ("r2", np.float32), ("pad", np.float32, 3)])        # agpt_sphere
+PLANE_DTYPE = np.dtype([("o", np.float32, 3), ("half_x", np.float32), ("half_z", np.float32), ("pad", np.float32, 3)])     # agpt_plane
+LIGHT_DTYPE = np.dtype([("type", np.int32), ("prim", np.int32), ("pad", np.float32, 2), ("lemit", np.float32, 3), ("pad2", np.float32)])   # agpt_light
+NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("first", np.int32), ("count", np.int32)])        # agpt_bvh_node
+PRIM_SPHERE, PRIM_PLANE, PRIM_BVH_MESH, PRIM_MESH = 0, 1, 2, 3
+LIGHT_AREA, LIGHT_UNIFORM_INFINITE, LIGHT_INFINITE_AREA = 0, 1, 2
+
+
+class RawMesh:
+    """One agpt_mesh_desc built from numpy arrays (kept alive here): nodes = NODE_DTYPE array or None,
+    tri_verts = [n, 3, 4] float32 (leaf order), tri_ids = [n] int32, optional normals [n, 3, 4] / uvs [n, 3, 2]."""
+
+    def __init__(self, tri_verts, tri_ids=None, nodes=None, normals=None, uvs=None):
+        self.verts = np.ascontiguousarray(tri_verts, np.float32).reshape(-1, 3, 4)
+        n = len(self.verts)
+        self.ids = np.ascontiguousarray(np.arange(n) if tri_ids is None else tri_ids, np.int32)
+        self.nodes = None if nodes is None else np.ascontiguousarray(nodes, NODE_DTYPE)
+        self.normals = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(n, 3, 4)
+        self.uvs = None if uvs is None else np.ascontiguousarray(uvs, np.float32).reshape(n, 3, 2)
+
+    def desc(self):
+        ptr = lambda a: None if a is None else a.ctypes.data
+        return MeshDesc(ptr(self.nodes), 0 if self.nodes is None else len(self.nodes), len(self.verts), ptr(self.verts), ptr(self.ids),
+                        ptr(self.normals), ptr(self.uvs))
+
+
 class Stats(ctypes.Structure):  # agpt_stats
     _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "rays_mis_culled", "rays_tail_culled")] + \
                [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests")] + \
@@ -146,6 +182,27 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         _check(core().agpt_set_stream(self._h, c_void_p(cuda_stream_ptr)))
+
+    # ---- raw table upload (what Scene::Flatten feeds the C ABI; tests build tables by hand) ----------
+    def upload_meshes(self, meshes):
+        descs = (MeshDesc * max(len(meshes), 1))(*[m.desc() for m in meshes])
+        _check(core().agpt_upload_meshes(self._h, descs, c_int(len(meshes))))
+
+    def upload_table(self, kind, rows):
+        """kind in spheres / planes / primitives / materials / lights; rows = structured numpy array (or Material list)."""
+        fn = getattr(core(), "agpt_upload_" + kind)
+        if kind == "materials":
+            arr = (Material * max(len(rows), 1))(*rows)
+            _check(fn(self._h, arr, c_int(len(rows))))
+            return
+        dt = {"spheres": SPHERE_DTYPE, "planes": PLANE_DTYPE, "primitives": PRIM_DTYPE, "lights": LIGHT_DTYPE}[kind]
+        rows = np.ascontiguousarray(rows, dt)
+        _check(fn(self._h, rows.ctypes.data_as(c_void_p), c_int(len(rows))))
+
+    def set_camera(self, cam19):
+        cam19 = np.ascontiguousarray(cam19, np.float32)
+        assert cam19.size == 19
+        _check(core().agpt_set_camera(self._h, _fptr(cam19)))
 
     def set_film(self, width, height):
         _check(core().agpt_set_film(self._h, c_int(width), c_int(height)))

@@ -53,9 +53,7 @@ int agpt_host_scene_destroy(agpt_host_scene* s) { delete s; return AGPT_OK; }
 
 int agpt_host_config_defaults(int config, int* out5, const char** name) {
 	agpt_scenes::ConfigDefaults d = agpt_scenes::Defaults(config);
-	if (d.width == 0 && config != 6 && config != 7) return HostFail("unknown configuration");
-	if (config == 6) d = { 320, 180, 16, 5, 0, "cfg6_corner_cases" };
-	if (config == 7) d = { 400, 400, 64, 5, 0, "cfg7_simple_test_scene_envmap_400x400" };
+	if (d.width == 0) return HostFail("unknown configuration");
 	out5[0] = d.width; out5[1] = d.height; out5[2] = d.spp; out5[3] = d.max_depth; out5[4] = d.depth_arg;
 	if (name) *name = d.name;
 	return AGPT_OK;

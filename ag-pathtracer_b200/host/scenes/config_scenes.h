@@ -38,6 +38,9 @@ inline ConfigDefaults Defaults(int config) {
 	case 3: return { 1920, 1080, 256, 8, 0, "cfg3_disney_multimaterial_1p31M_1080p_256spp_depth8" };
 	case 4: return { 3840, 2160, 1024, 8, 0, "cfg4_8xicosphere_10p5M_4k_1024spp_depth8" };
 	case 5: return { 1920, 1080, 64, 16, 4, "cfg5_closed_box_incoherent_1080p_depth16_rr" };
+	case 6: return { 320, 180, 16, 5, 0, "cfg6_test_thin_lens_plain_mesh_multi_tri_leaves" };
+	case 7: return { 400, 400, 64, 5, 0, "cfg7_reference_default_scene_envmap_400x400" };
+	case 8: return { 640, 360, 16, 6, 4, "cfg8_test_degenerate_triangles_deep_tree_overflowing_light" };
 	default: return { 0, 0, 0, 0, 0, "unknown" };
 	}
 }
@@ -377,6 +380,94 @@ inline void BuildConfig7(Scene* scene) {
 	scene->lights.push_back(std::make_shared<InfiniteAreaLight>(path));
 }
 
+// cfg 8 (test-only): the branches no other configuration reaches.
+//   * a BVHTriMesh whose SAH tree is a CHAIN: 30 equal triangles perpendicular to x at x = 1e-18 * 16^i.
+//     Every binned split (bvhtrimesh.h:257-300) peels off the farthest one, so the tree is 29 levels
+//     deep and a ray along +x hits both children at every level: 29 pending far children, more than
+//     the traversal keeps in shared memory.  The first ten triangles lie within one ulp of x = 0 as
+//     seen from a ray origin at x = -1: exact-t ties, decided by visit order;
+//   * a plain TriangleMesh BETWEEN two BVH meshes and another after them (one run of four mesh
+//     primitives), the first holding the
+//     triangles TriangleIntersect rejects or special-cases (trianglemesh.cpp:59-80): zero area, an
+//     area so small that |ng|^2 underflows while det != 0 (dropped by Intersect, kept by
+//     IntersectP), zero-determinant texture coordinates on sound geometry (CoordinateSystem
+//     fallback), collinear texture coordinates;
+//   * a large sphere light with Lemit 3e38: next-event estimates near it overflow to inf, and
+//     inf times a zero throughput channel (after the magenta mirror) is NaN -- the samples
+//     MyApp::Tick zeroes (myapp.cpp:169-172);
+//   * Russian roulette live (depth argument 4), mirror sphere, two infinite lights in one scene.
+inline void BuildConfig8(Scene* scene, int level) {
+	auto grey = DisneyMaterial::Make(float3(.6f, .6f, .6f), 1.f, 0.f);
+	scene->primitives.push_back(std::make_shared<Plane>(float3(0, -1, 0), float2(30, 30), grey));
+	auto red = DisneyMaterial::Make(float3(1.f, 0.f, 0.f), 1.f, 0.f);
+	{
+		std::vector<float3> vertices, normals;
+		std::vector<float2> texcoords;
+		std::vector<index_type> indices;
+		float x = 1e-18f;
+		for (int i = 0; i < 30; i++, x *= 16.f) {
+			int base = (int)vertices.size();
+			vertices.push_back(float3(x, -1.f, 5.f)); vertices.push_back(float3(x, 1.f, 5.f)); vertices.push_back(float3(x, 0.f, 7.f));
+			for (int k = 0; k < 3; k++) indices.push_back(index_type(base + k));
+		}
+		auto chain = std::make_shared<TriangleMesh>(indices, vertices, normals, texcoords, red);
+		scene->primitives.push_back(std::make_shared<BVHTriMesh>(chain, red, 1));
+	}
+	auto cream = DisneyMaterial::Make(hex2lin(0xf6e7d0), .6f, 0.f);
+	{
+		std::vector<float3> vertices, normals;
+		std::vector<float2> texcoords;
+		std::vector<index_type> indices;
+		auto tri = [&](float3 a, float3 b, float3 c, float2 ta, float2 tb, float2 tc) {
+			int base = (int)vertices.size();
+			vertices.push_back(a); vertices.push_back(b); vertices.push_back(c);
+			texcoords.push_back(ta); texcoords.push_back(tb); texcoords.push_back(tc);
+			for (int k = 0; k < 3; k++) { index_type idx(base + k); idx.texcoord_index = base + k; indices.push_back(idx); }
+		};
+		// a sound quad with sound texture coordinates
+		tri(float3(-4.f, -1.f, 2.f), float3(-2.f, -1.f, 2.f), float3(-2.f, 1.5f, 2.5f), float2(0, 0), float2(1, 0), float2(1, 1));
+		tri(float3(-4.f, -1.f, 2.f), float3(-2.f, 1.5f, 2.5f), float3(-4.f, 1.5f, 2.5f), float2(0, 0), float2(1, 1), float2(0, 1));
+		// zero area (two equal vertices): det == 0 for every ray
+		tri(float3(-3.f, 0.f, 1.f), float3(-3.f, 0.f, 1.f), float3(-2.5f, 1.f, 1.f), float2(0, 0), float2(1, 0), float2(1, 1));
+		// |ng|^2 underflows to 0 although det != 0: rejected by TriangleIntersect only after the t test,
+		// accepted by TriangleIntersectP.  Texture coordinates degenerate so the ng branch is taken.
+		tri(float3(0.f, 0.f, 0.f), float3(1e-12f, 0.f, 0.f), float3(0.f, 1e-12f, 0.f), float2(.5f, .5f), float2(.5f, .5f), float2(.5f, .5f));
+		// sound geometry, all three texture coordinates equal: CoordinateSystem(normalize(ng)) frame
+		tri(float3(-1.5f, -1.f, 3.f), float3(.5f, -1.f, 3.f), float3(-.5f, 1.2f, 3.4f), float2(.5f, .5f), float2(.5f, .5f), float2(.5f, .5f));
+		// sound geometry, collinear texture coordinates: same branch through a zero determinant
+		tri(float3(1.f, -1.f, 3.f), float3(3.f, -1.f, 3.f), float3(2.f, 1.2f, 3.4f), float2(0, 0), float2(1, 1), float2(2, 2));
+		scene->primitives.push_back(std::make_shared<TriangleMesh>(indices, vertices, normals, texcoords, cream));   // plain: brute force
+	}
+	auto teal = DisneyMaterial::Make(float3(.1f, .6f, .55f), .35f, .5f);
+	auto ball = MakeIcosphere(level, float3(3.f, 0.f, 0.f), 1.f, teal);
+	scene->primitives.push_back(std::make_shared<BVHTriMesh>(ball, teal, 1));
+	{
+		// magenta mirror wall behind the overflowing light: throughput (.9, 0, .9), and what it reflects
+		// is the floor around the light -- 0 * inf = NaN in the green channel
+		auto magenta = MirrorMaterial::Make(float3(.9f, 0.f, .9f));
+		std::vector<float3> vertices, normals;
+		std::vector<float2> texcoords;
+		std::vector<index_type> indices;
+		vertices.push_back(float3(-4.f, -1.f, 11.5f)); vertices.push_back(float3(4.f, -1.f, 11.5f));
+		vertices.push_back(float3(4.f, 3.f, 11.5f)); vertices.push_back(float3(-4.f, 3.f, 11.5f));
+		const int order[6] = { 0, 1, 2, 0, 2, 3 };
+		for (int o : order) indices.push_back(index_type(o));
+		scene->primitives.push_back(std::make_shared<TriangleMesh>(indices, vertices, normals, texcoords, magenta));
+	}
+	auto mirror = MirrorMaterial::Make(float3(.9f, .9f, .9f));
+	scene->primitives.push_back(std::make_shared<Sphere>(float3(-1.2f, 0.f, -1.f), 1.f, mirror));
+	scene->addAreaLight(std::make_shared<Sphere>(float3(0.f, .4f, 9.f), 1.4f, nullptr), float3(3e38f, 3e38f, 3e38f));   // rests on the floor behind the chain; estimates near it overflow
+	scene->addAreaLight(std::make_shared<Sphere>(float3(0, 8, -4), .5f, nullptr), WarmWhite(150));
+	scene->lights.push_back(std::make_shared<UniformInfiniteLight>(float3(.25f, .28f, .32f)));
+	scene->lights.push_back(std::make_shared<UniformInfiniteLight>(float3(.05f, .04f, .03f)));
+	scene->camera.lookfrom = float3(4.5f, 2.5f, -8.f);      // off axis: the chain triangles (planes x = const) are seen obliquely
+	scene->camera.lookat = float3(0, 0, 2.f);
+	scene->camera.vup = float3(0, 1, 0);
+	scene->camera.aspect_ratio = 16.f / 9.f;
+	scene->camera.vfov = 40;
+	scene->camera.aperture = 0;
+}
+
 // level <= 0 selects the BASELINE.json size of each configuration.
 inline bool BuildConfig(Scene* scene, int config, int level) {
 	switch (config) {
@@ -387,6 +478,7 @@ inline bool BuildConfig(Scene* scene, int config, int level) {
 	case 5: BuildConfig5(scene, level > 0 ? level : 7); return true;
 	case 6: BuildConfig6(scene, level > 0 ? level : 2); return true;
 	case 7: BuildConfig7(scene); return true;
+	case 8: BuildConfig8(scene, level > 0 ? level : 3); return true;
 	default: return false;
 	}
 }

@@ -24,7 +24,7 @@ typedef struct agpt_host_tracer agpt_host_tracer;
 
 const char* agpt_host_last_error(void);
 
-/* config 1..5 = BASELINE.json configs[0..4], 6 = test-only corner-case scene;
+/* config 1..5 = BASELINE.json configs[0..4]; 6 and 8 = test-only corner-case scenes, 7 = the reference default scene;
  * level <= 0 picks the configuration's own icosphere subdivision level. */
 int agpt_host_scene_create(int config, int level, agpt_host_scene** out);
 int agpt_host_scene_destroy(agpt_host_scene* scene);

@@ -947,6 +947,28 @@ long long agpt_oracle_primary_hits(void* h, int W, int H, int sample, int thread
 	return 0;
 }
 
+// Scene::Intersect / IntersectP for caller rays (O, D normalised like the Ray ctor, tmax): same
+// contract as agpt_ref_trace_rays.  counters_out (optional, 3): interior visits, box tests, triangle tests.
+void agpt_oracle_trace_rays(void* h, long long n, const float* rays7, int any_hit, agpt_hit* out, unsigned long long* counters_out) {
+	const OScene& sc = *(OScene*)h;
+	Counters c;
+	for (long long i = 0; i < n; i++) {
+		const float* r = rays7 + 7 * i;
+		Ray ray(v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), r[6]);
+		agpt_hit& o = out[i];
+		o.prim = -1; o.tri = -1; o.t = 0.f;
+		if (any_hit) { o.found = SceneIntersectP(sc, ray, c) ? 1u : 0u; continue; }
+		Hit hit;
+		bool found = SceneIntersect(sc, ray, hit, c);
+		o.found = found ? 1u : 0u;
+		if (found) {
+			o.prim = hit.prim; o.t = hit.t;
+			o.tri = hit.slot >= 0 ? sc.meshes[sc.prims[hit.prim].payload].ids[hit.slot] : -1;
+		}
+	}
+	if (counters_out) { counters_out[0] = c.interior; counters_out[1] = c.boxes; counters_out[2] = c.tris; }
+}
+
 // radiance + number of RandomFloat() draws of single camera paths
 void agpt_oracle_li_pixels(void* h, int W, int H, int n, const int* xs, const int* ys, const int* ss, int max_depth, int depth_arg,
 		float* out_rgb, int* draws_out) {

@@ -32,12 +32,49 @@ def _fp(a):
     return a.ctypes.data_as(POINTER(c_float))
 
 
-class PortScene:
-    """The restatement fed with the flattened tables of a host-mirror scene (HostScene.tables())."""
+class _Tables(ctypes.Structure):       # agpt_oracle_tables (= agpt_scene_tables of include/agpt_host.h)
+    _fields_ = [("prims", c_void_p), ("n_prims", c_int), ("spheres", c_void_p), ("n_spheres", c_int), ("planes", c_void_p), ("n_planes", c_int),
+                ("meshes", c_void_p), ("n_meshes", c_int), ("materials", c_void_p), ("n_materials", c_int), ("lights", c_void_p), ("n_lights", c_int),
+                ("camera", c_float * 19), ("env_w", c_int), ("env_h", c_int), ("env_rgb", c_void_p), ("env_func", c_void_p), ("env_cdf", c_void_p),
+                ("env_func_int", c_float)]
 
-    def __init__(self, host_scene):
-        self._keep = host_scene                      # the tables borrow the host scene's memory
-        self._h = c_void_p(lib().agpt_oracle_scene_create(host_scene.tables()))
+
+class PortScene:
+    """The restatement fed with the flattened tables of a host-mirror scene (HostScene.tables()),
+    or with hand-built tables (PortScene.from_tables)."""
+
+    def __init__(self, host_scene=None, tables=None, keep=None):
+        self._keep = host_scene if host_scene is not None else keep       # the tables borrow this memory
+        self._h = c_void_p(lib().agpt_oracle_scene_create(host_scene.tables() if host_scene is not None else ctypes.byref(tables)))
+
+    @classmethod
+    def from_tables(cls, prims, meshes=(), spheres=None, planes=None, materials=(), lights=None, camera=None):
+        """prims / spheres / planes / lights: structured numpy arrays in the layouts of include/agpt.h;
+        meshes: objects with .desc() -> agpt_mesh_desc (binding.RawMesh); materials: list of agpt_material."""
+        t = _Tables()
+        keep = [prims, meshes, spheres, planes, materials, lights]
+        def put(name, count, arr):
+            setattr(t, name, arr.ctypes.data if arr is not None and len(arr) else None)
+            setattr(t, count, 0 if arr is None else len(arr))
+        put("prims", "n_prims", prims); put("spheres", "n_spheres", spheres); put("planes", "n_planes", planes); put("lights", "n_lights", lights)
+        if len(meshes):
+            descs = (type(meshes[0].desc()) * len(meshes))(*[m.desc() for m in meshes])
+            keep.append(descs)
+            t.meshes = ctypes.addressof(descs); t.n_meshes = len(meshes)
+        if len(materials):
+            mats = (type(materials[0]) * len(materials))(*materials)
+            keep.append(mats)
+            t.materials = ctypes.addressof(mats); t.n_materials = len(materials)
+        if camera is not None:
+            t.camera = (c_float * 19)(*[float(v) for v in camera])
+        return cls(tables=t, keep=keep)
+
+    def trace_rays(self, rays7, any_hit=False):
+        rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
+        hits = np.zeros(len(rays7), HIT_DTYPE)
+        st = (c_ulonglong * 3)()
+        lib().agpt_oracle_trace_rays(self._h, c_longlong(len(rays7)), _fp(rays7), c_int(1 if any_hit else 0), hits.ctypes.data_as(c_void_p), st)
+        return hits, dict(interior=st[0], boxes=st[1], tris=st[2])
 
     def close(self):
         if self._h:

@@ -19,8 +19,16 @@ from oracle import ref_binding as ref  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 # (config, icosphere level, W, H, spp) -- small enough to commit, every code path covered
-CASES = [(1, 0, 64, 36, 4), (2, 3, 64, 36, 2), (3, 2, 64, 36, 2), (4, 2, 64, 36, 2), (5, 2, 64, 36, 2), (6, 2, 64, 36, 4), (7, 0, 48, 48, 4)]
-DEFAULTS = {1: (5, 0), 2: (1, 0), 3: (8, 0), 4: (8, 0), 5: (16, 4), 6: (5, 0), 7: (5, 0)}   # max_depth, depth_arg (config_scenes.h)
+CASES = [(1, 0, 64, 36, 4), (2, 3, 64, 36, 2), (3, 2, 64, 36, 2), (4, 2, 64, 36, 2), (5, 2, 64, 36, 2), (6, 2, 64, 36, 4), (7, 0, 48, 48, 4),
+         (8, 3, 96, 54, 4)]
+DEFAULTS = {1: (5, 0), 2: (1, 0), 3: (8, 0), 4: (8, 0), 5: (16, 4), 6: (5, 0), 7: (5, 0), 8: (6, 4)}   # max_depth, depth_arg (config_scenes.h)
+
+# cfg 8: rays no camera produces -- along +x and -x through all 30 chain triangles (29 pending far
+# children; ten exact-t ties), and through the triangle whose |ng|^2 underflows, once with the ray
+# extent beyond it (TriangleIntersect drops it, TriangleIntersectP keeps it) and once short of it.
+CFG8_RAYS = [[-1, .1, 5.9, 1, 0, 0, 3.0e38], [-1, -.3, 6.2, 1, 0, 0, 3.0e38], [1e18, .1, 5.9, -1, 0, 0, 3.0e38], [-1, .1, 5.9, 1, 1e-3, 0, 3.0e38],
+             [2.5e-13, 2.5e-13, -1, 0, 0, 1, 3.0e38], [2.5e-13, 2.5e-13, -1, 0, 0, 1, 1.05], [2.5e-13, 2.5e-13, -1, 0, 0, 1, .9999],
+             [-2.8, .4, -1, 0, 0, 1, 3.0e38]]
 
 
 def sha(a):
@@ -41,6 +49,15 @@ def scene_fixture(cfg, level, W, H, spp):
     # single paths: radiance + RNG draw counts (draw-order conformance)
     rng = np.random.RandomState(cfg)
     xs = rng.randint(0, W, 48).astype(np.int32); ys = rng.randint(0, H, 48).astype(np.int32); ss = rng.randint(0, 1000, 48).astype(np.int32)
+    if cfg == 8:
+        # add paths whose radiance is inf or NaN (the samples myapp.cpp:169-172 zeroes), found by scanning the film
+        gx, gy = np.meshgrid(np.arange(W, dtype=np.int32), np.arange(H, dtype=np.int32))
+        gx, gy = gx.ravel(), gy.ravel()
+        for s in range(12):
+            scan = rs.li_pixels(W, H, gx, gy, np.full_like(gx, s), md, da)
+            bad = np.flatnonzero(np.isnan(scan).any(1))
+            bad = np.concatenate([bad, np.flatnonzero(np.isinf(scan).any(1) & ~np.isnan(scan).any(1))[:4]])
+            xs = np.concatenate([xs, gx[bad]]); ys = np.concatenate([ys, gy[bad]]); ss = np.concatenate([ss, np.full(len(bad), s, np.int32)])
     li, draws = rs.li_pixels(W, H, xs, ys, ss, md, da, want_draws=True)
     d["li_xs"], d["li_ys"], d["li_ss"], d["li"], d["li_draws"] = xs, ys, ss, li, draws
     # scene construction: per primitive kind / material constants / BVH digests
@@ -63,6 +80,8 @@ def scene_fixture(cfg, level, W, H, spp):
     dd = rng.normal(size=(256, 3)).astype(np.float32)
     tm = np.where(rng.rand(256) < 0.5, np.float32(3.4028235e38), rng.uniform(0.5, 20, 256)).astype(np.float32)
     r7 = np.concatenate([o, dd, tm[:, None]], 1).astype(np.float32)
+    if cfg == 8:
+        r7 = np.concatenate([np.array(CFG8_RAYS, np.float32), r7])
     d["probe_rays"] = r7
     d["probe_closest"], _ = rs.trace_rays(r7, any_hit=False)
     d["probe_any"], _ = rs.trace_rays(r7, any_hit=True)
@@ -133,6 +152,9 @@ def function_fixture():
 
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
+    only = [int(a) for a in sys.argv[1:]]          # e.g. `make_golden.py 8` regenerates scene_cfg8.npz alone
     for case in CASES:
-        scene_fixture(*case)
-    function_fixture()
+        if not only or case[0] in only:
+            scene_fixture(*case)
+    if not only:
+        function_fixture()

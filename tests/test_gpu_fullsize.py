@@ -19,13 +19,15 @@ def ctx2(agpt):
     ctx.close()
 
 
-@pytest.mark.parametrize("cfg", [2, 3])
+@pytest.mark.parametrize("cfg", [2, 3, 5, 4])
 def test_full_size_primary_hits_bit_exact(agpt, ref, ctx2, cfg):
-    """1080p, 1.31 M triangles: hit flag, primitive id, triangle id and t bits of every pixel."""
+    """BASELINE sizes (1080p with 1.31 M triangles; cfg 5's closed room; cfg 4: 4K, 10.5 M triangles in
+    eight meshes): hit flag, primitive id, triangle id and t bits of every pixel, and the walk's
+    visit / box / triangle counts against the reference's instrumented walk."""
     d = agpt.config_defaults(cfg)
     W, H = d["width"], d["height"]
     hs = agpt.HostScene(cfg, 0); rs = ref.RefScene(cfg, 0)
-    assert hs.counts()["tris"] >= 1310720
+    assert hs.counts()["tris"] >= {2: 1310720, 3: 1310720, 4: 10485760, 5: 655360}[cfg]
     hs.upload(ctx2); ctx2.set_film(W, H)
     want, st = rs.primary_hits(W, H, 0)
     assert st["walk_mismatches"] == 0
@@ -73,3 +75,44 @@ def test_full_size_radiance_crop_vs_reference(agpt, ref, ctx2):
     exact = np.mean(np.all(gv == wv, axis=-1))
     print(f"full-size crop: rel-RMSE {err:.3e}, bit-identical pixels {exact:.4f}")
     assert err <= 1e-3
+
+
+@pytest.mark.parametrize("cfg,spp", [(4, 2), (5, 4)])
+def test_full_size_radiance_crop_cfg4_cfg5(agpt, ref, ctx2, cfg, spp):
+    """cfg 4 (4K, eight 1.31 M-triangle meshes, 8 bounces) and cfg 5 (1080p closed room, 16 bounces, Russian
+    roulette live): a centred 256x144 crop of the full-size frame against the reference, same streams."""
+    d = agpt.config_defaults(cfg)
+    W, H, md, da = d["width"], d["height"], d["max_depth"], d["depth_arg"]
+    hs = agpt.HostScene(cfg, 0); rs = ref.RefScene(cfg, 0)
+    hs.upload(ctx2); ctx2.set_film(W, H); ctx2.clear()
+    ctx2.render(0, spp, md, da)
+    got = ctx2.read_accum()
+    x0, y0, x1, y1 = (W - 256) // 2, (H - 144) // 2, (W + 256) // 2, (H + 144) // 2
+    want, _ = rs.render(W, H, 0, spp, md, da, crop=(x0, y0, x1, y1))
+    gv = got[::-1][y0:y1, x0:x1, :3]; wv = want[::-1][y0:y1, x0:x1, :3]
+    err = float(np.sqrt(np.mean((gv.astype(np.float64) - wv.astype(np.float64)) ** 2)) / np.mean(np.abs(wv)))
+    exact = np.mean(np.all(bits(gv) == bits(wv), axis=-1))
+    print(f"cfg{cfg} full-size crop: rel-RMSE {err:.3e}, bit-identical pixels {exact:.4f}")
+    assert err <= 1e-3
+    assert exact >= 0.999
+
+
+def test_cfg1_whole_frame_at_its_own_size(agpt, ref, ctx2):
+    """BASELINE configs[0] as written: 640x360, 64 spp, PathTracer(5) -- the whole film against the reference
+    CPU integrator (14.7 M reference paths: seconds on the box's cores)."""
+    d = agpt.config_defaults(1)
+    W, H, spp, md, da = d["width"], d["height"], d["spp"], d["max_depth"], d["depth_arg"]
+    assert (W, H, spp) == (640, 360, 64)
+    hs = agpt.HostScene(1, 0); rs = ref.RefScene(1, 0)
+    hs.upload(ctx2); ctx2.set_film(W, H); ctx2.clear()
+    ctx2.render(0, spp, md, da)
+    got = ctx2.read_accum()
+    want, paths = rs.render(W, H, 0, spp, md, da)
+    assert paths == W * H * spp
+    err = float(np.sqrt(np.mean((got[..., :3].astype(np.float64) - want[..., :3].astype(np.float64)) ** 2)) / np.mean(np.abs(want[..., :3])))
+    exact = np.mean(np.all(bits(got[..., :3]) == bits(want[..., :3]), axis=-1))
+    print(f"cfg1 640x360x64: rel-RMSE {err:.3e}, bit-identical pixels {exact:.5f}")
+    assert err <= 1e-3
+    assert exact >= 0.999
+    # and the displayed image: CopyToSurface bytes
+    assert np.array_equal(ctx2.resolve(spp), ref.resolve(got, spp))

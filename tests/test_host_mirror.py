@@ -13,7 +13,7 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_mirror_matches_golden(agpt, cfg):
     g = np.load(os.path.join(GOLDEN, f"scene_cfg{cfg}.npz"))
     level = int(g["case"][1])

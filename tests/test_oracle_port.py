@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = [1, 2, 3, 4, 5, 6, 7]
+CASES = [1, 2, 3, 4, 5, 6, 7, 8]
 
 
 def bits(a):
@@ -48,7 +48,7 @@ def test_port_matches_golden(agpt, port, cfg):
 def test_port_matches_reference_live(agpt, port, ref, cfg):
     """Fresh seeds / sizes against the compiled reference (skipped where oracle/_ref is absent)."""
     d = agpt.config_defaults(cfg)
-    level = {1: 0, 2: 4, 3: 3, 4: 2, 5: 3, 6: 2, 7: 0}[cfg]
+    level = {1: 0, 2: 4, 3: 3, 4: 2, 5: 3, 6: 2, 7: 0, 8: 2}[cfg]
     W, H, spp = 96, 54, 3
     hs = agpt.HostScene(cfg, level); rs = ref.RefScene(cfg, level); ps = port.PortScene(hs)
     a, _ = rs.render(W, H, 5, spp, d["max_depth"], d["depth_arg"])
