@@ -75,7 +75,8 @@ class Stats(ctypes.Structure):  # agpt_stats
     _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "rays_mis_culled", "rays_tail_culled")] + \
                [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests")] + \
                [(n, c_uint64) for n in ("kernel_launches", "launches_closest", "launches_any", "launches_shade", "waves")] + \
-               [(n, c_float) for n in ("ms_render", "ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other")]
+               [(n, c_float) for n in ("ms_render", "ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other", "ms_reduce")] + \
+               [("reduce_path", c_uint32)]
 
     def as_dict(self):
         d = {}
@@ -274,6 +275,29 @@ class Context:
     def reset_stats(self):
         _check(core().agpt_reset_stats(self._h))
 
+    # ---- multi-process sharding: peers' accumulators through CUDA IPC ---------------------------
+    def accum_ipc_handle(self):
+        buf = ctypes.create_string_buffer(64)
+        _check(core().agpt_accum_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def open_peer_accums(self, rank, handles):
+        """handles: list of 64-byte handles in rank order (own entry ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        _check(core().agpt_open_peer_accums(self._h, c_int(rank), c_int(len(handles)), blob))
+
+    def close_peer_accums(self):
+        _check(core().agpt_close_peer_accums(self._h))
+
+    def allreduce_accum_peers(self):
+        _check(core().agpt_allreduce_accum_peers(self._h))
+
+    def reduce_resolve_peers(self, samples, keep_sum=False):
+        out = np.empty((self.height, self.width), np.uint32)
+        _check(core().agpt_reduce_resolve_peers(self._h, c_int(samples), c_int(1 if keep_sum else 0), out.ctypes.data_as(POINTER(c_uint32))))
+        return out
+
     def debug_status(self):
         out = (c_uint64 * 4)()
         _check(core().agpt_debug_status(self._h, out))
@@ -308,6 +332,30 @@ class Context:
     def probe_stream(self, pixel_index, sample, k):
         out = np.empty(k, np.float32)
         _check(core().agpt_probe_stream(self._h, c_uint32(pixel_index), c_uint32(sample), c_int(k), _fptr(out)))
+        return out
+
+
+class Group:
+    """Contexts of this process, one per GPU, that split a render by sample index."""
+
+    def __init__(self, contexts):
+        self.contexts = list(contexts)
+        self._arr = (c_void_p * len(self.contexts))(*[c.handle for c in self.contexts])
+
+    def __len__(self):
+        return len(self.contexts)
+
+    def render(self, first_sample, num_samples, max_depth, depth_arg=0, flags=0):
+        _check(core().agpt_render_multi(self._arr, c_int(len(self)), c_int(first_sample), c_int(num_samples), c_int(max_depth), c_int(depth_arg), c_uint32(flags)))
+
+    def reduce(self, root=-1):
+        """Sum of the accumulators, in rank order: into every context (root = -1) or into contexts[root] only."""
+        _check(core().agpt_reduce_accum(self._arr, c_int(len(self)), c_int(root)))
+
+    def reduce_resolve(self, samples, keep_sum=False):
+        c0 = self.contexts[0]
+        out = np.empty((c0.height, c0.width), np.uint32)
+        _check(core().agpt_reduce_resolve(self._arr, c_int(len(self)), c_int(samples), c_int(1 if keep_sum else 0), out.ctypes.data_as(POINTER(c_uint32))))
         return out
 
 
@@ -429,9 +477,13 @@ class HostScene:
 class HostTracer:
     """CudaPathTracer: the reference-facing integrator object (host buffers in and out)."""
 
-    def __init__(self, max_depth=5, device=0):
+    def __init__(self, max_depth=5, device=0, devices=None):
         self._h = c_void_p()
-        _check(host().agpt_host_tracer_create(c_int(max_depth), c_int(device), byref(self._h)), host_side=True)
+        if devices is None:
+            _check(host().agpt_host_tracer_create(c_int(max_depth), c_int(device), byref(self._h)), host_side=True)
+        else:
+            arr = (c_int * len(devices))(*devices)
+            _check(host().agpt_host_tracer_create_multi(c_int(max_depth), arr, c_int(len(devices)), byref(self._h)), host_side=True)
 
     def close(self):
         if self._h:
@@ -449,6 +501,15 @@ class HostTracer:
         _check(host().agpt_host_tracer_render(self._h, scene.handle, c_int(width), c_int(height), _fptr(accum), c_int(first_sample),
                                               c_int(num_samples), c_int(depth_arg), c_uint32(flags), c_int(1 if reupload else 0)), host_side=True)
         return accum
+
+    def render_resolve(self, scene, width, height, accum, samples_so_far, first_sample, num_samples, depth_arg=0, flags=0):
+        """RenderAndResolve: returns the packed 0x00RRGGBB image of the film after these samples."""
+        assert accum.dtype == np.float32 and accum.shape == (height, width, 4) and accum.flags.c_contiguous
+        out = np.empty((height, width), np.uint32)
+        _check(host().agpt_host_tracer_render_resolve(self._h, scene.handle, c_int(width), c_int(height), _fptr(accum), c_int(samples_so_far),
+                                                      c_int(first_sample), c_int(num_samples), c_int(depth_arg), c_uint32(flags),
+                                                      out.ctypes.data_as(POINTER(c_uint32))), host_side=True)
+        return out
 
     def li(self, scene, origin, direction, depth_arg=0):
         o = (c_float * 3)(*origin); d = (c_float * 3)(*direction); out = (c_float * 3)()

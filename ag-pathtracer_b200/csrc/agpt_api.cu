@@ -6,10 +6,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
 #include "agpt_kernels.cuh"
+#include "agpt_multigpu.cuh"
 
 // ---- error plumbing ----------------------------------------------------------------------
 static thread_local std::string g_error;
@@ -111,6 +113,10 @@ struct agpt_ctx {
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned ring of kRing x 3 ints
 	cudaEvent_t ringEvents[8] = {};
+
+	// multi-process sharding: the other ranks' accumulators, mapped through CUDA IPC (agpt_open_peer_accums)
+	float4* peerAccum[AGPT_MAX_PEERS] = {};
+	int peerRank = -1, peerWorld = 0;
 
 	agpt_stats stats;
 	bool asyncWaves = false;      // AGPT_ASYNC_WAVES=1: run one wave ahead of the landed queue counts instead of syncing
@@ -328,6 +334,7 @@ int agpt_destroy(agpt_ctx* c) {
 	if (!c) return AGPT_OK;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	for (int r = 0; r < c->peerWorld; r++) if (r != c->peerRank && c->peerAccum[r]) cudaIpcCloseMemHandle(c->peerAccum[r]);
 	for (auto& m : c->meshStore) m.Free();
 	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free(); c->resolved.Free();
@@ -933,6 +940,278 @@ int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_sta
 	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
 	rays.Free(); seeds.Free();
 	return rcode;
+}
+
+// ---- multi-GPU: sample-index sharding ---------------------------------------------
+// One context per GPU, every context holds the whole scene; GPU g renders s = first + g, first + g + G, ...
+static int CheckGroup(agpt_ctx** ctxs, int n) {
+	NEED(ctxs != nullptr && n >= 1 && n <= AGPT_MAX_PEERS, AGPT_ERR_INVALID, "bad context list (1.." + std::to_string(AGPT_MAX_PEERS) + " contexts)");
+	for (int g = 0; g < n; g++) {
+		NEED(ctxs[g] != nullptr && ctxs[g]->accum != nullptr, AGPT_ERR_STATE, "context " + std::to_string(g) + ": film not set");
+		NEED(ctxs[g]->width == ctxs[0]->width && ctxs[g]->height == ctxs[0]->height, AGPT_ERR_INVALID, "contexts have different film sizes");
+		for (int h = 0; h < g; h++) NEED(ctxs[h] != ctxs[g] && ctxs[h]->device != ctxs[g]->device, AGPT_ERR_INVALID, "two contexts on one GPU");
+	}
+	return AGPT_OK;
+}
+
+// Peer access between every pair of the group's GPUs; *all = false if some pair has none.
+static int EnablePeerAccess(agpt_ctx** ctxs, int n, bool* all) {
+	*all = true;
+	for (int a = 0; a < n; a++)
+		for (int b = 0; b < n; b++) {
+			if (a == b) continue;
+			int can = 0;
+			CU(cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device));
+			if (!can) { *all = false; continue; }
+			CU(cudaSetDevice(ctxs[a]->device));
+			cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b]->device, 0);
+			if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+			else if (e != cudaSuccess) return Fail(AGPT_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+		}
+	return AGPT_OK;
+}
+
+static int SyncGroup(agpt_ctx** ctxs, int n) {
+	for (int g = 0; g < n; g++) { CU(cudaSetDevice(ctxs[g]->device)); CU(cudaStreamSynchronize(ctxs[g]->stream)); }
+	return AGPT_OK;
+}
+
+static NcclApi g_nccl;
+static std::vector<int> g_ncclDevices;
+static std::vector<agpt_ncclComm_t> g_ncclComms;
+
+static int NcclAllReduce(agpt_ctx** ctxs, int n) {
+	NEED(g_nccl.Load(), AGPT_ERR_STATE, g_nccl.error);
+	std::vector<int> devs(n);
+	for (int g = 0; g < n; g++) devs[g] = ctxs[g]->device;
+	if (devs != g_ncclDevices) {
+		for (auto cm : g_ncclComms) g_nccl.CommDestroy(cm);
+		g_ncclComms.assign(n, nullptr);
+		int r = g_nccl.CommInitAll(g_ncclComms.data(), n, devs.data());
+		if (r != 0) { g_ncclComms.clear(); g_ncclDevices.clear(); return Fail(AGPT_ERR_CUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r)); }
+		g_ncclDevices = devs;
+	}
+	const size_t count = 4 * (size_t)ctxs[0]->width * ctxs[0]->height;
+	int r = g_nccl.GroupStart();
+	for (int g = 0; g < n && r == 0; g++) {
+		CU(cudaSetDevice(ctxs[g]->device));
+		r = g_nccl.AllReduce(ctxs[g]->accum, ctxs[g]->accum, count, /*ncclFloat*/ 7, /*ncclSum*/ 0, g_ncclComms[g], ctxs[g]->stream);
+	}
+	int r2 = g_nccl.GroupEnd();
+	if (r != 0 || r2 != 0) return Fail(AGPT_ERR_CUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r != 0 ? r : r2));
+	return AGPT_OK;
+}
+
+static bool WantNccl() { const char* e = getenv("AGPT_REDUCE"); return e && std::string(e) == "nccl"; }
+
+static void SliceOf(int g, int n, size_t wh, int* first, int* count) {
+	size_t a = wh * (size_t)g / n, b = wh * (size_t)(g + 1) / n;
+	*first = (int)a; *count = (int)(b - a);
+}
+
+int agpt_reduce_accum(agpt_ctx** ctxs, int n, int root) {
+	int rcode = CheckGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(root >= -1 && root < n, AGPT_ERR_INVALID, "bad root");
+	if (n == 1) return AGPT_OK;
+	bool peers = false;
+	rcode = EnablePeerAccess(ctxs, n, &peers);
+	if (rcode != AGPT_OK) return rcode;
+	rcode = SyncGroup(ctxs, n);                    // every render has landed before any accumulator is read
+	if (rcode != AGPT_OK) return rcode;
+	const size_t wh = (size_t)ctxs[0]->width * ctxs[0]->height;
+	for (int g = 0; g < n; g++) { CU(cudaSetDevice(ctxs[g]->device)); CU(cudaEventRecord(ctxs[g]->evRender0, ctxs[g]->stream)); }
+	int path = 1;
+	if (!peers || WantNccl()) {
+		path = 2;
+		rcode = NcclAllReduce(ctxs, n);
+		if (rcode != AGPT_OK) return rcode;
+	}
+	else {
+		PeerAccums pa;
+		pa.n = n;
+		for (int g = 0; g < n; g++) pa.p[g] = ctxs[g]->accum;
+		for (int g = 0; g < n; g++) {
+			if (root >= 0 && g != root) continue;
+			int first = 0, count = (int)wh;
+			if (root < 0) SliceOf(g, n, wh, &first, &count);
+			CU(cudaSetDevice(ctxs[g]->device));
+			if (root < 0) k_allreduce_slice<<<Blocks(count, 256), 256, 0, ctxs[g]->stream>>>(pa, first, count);
+			else k_reduce_resolve<<<Blocks(count, 256), 256, 0, ctxs[g]->stream>>>(pa, first, count, 1.f, ctxs[g]->accum, nullptr);
+			CU(cudaGetLastError());
+			ctxs[g]->stats.kernel_launches++;
+		}
+	}
+	for (int g = 0; g < n; g++) { CU(cudaSetDevice(ctxs[g]->device)); CU(cudaEventRecord(ctxs[g]->evRender1, ctxs[g]->stream)); }
+	rcode = SyncGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	for (int g = 0; g < n; g++) {
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctxs[g]->evRender0, ctxs[g]->evRender1);
+		ctxs[g]->stats.ms_reduce += ms; ctxs[g]->stats.reduce_path = (uint32_t)path;
+	}
+	return AGPT_OK;
+}
+
+int agpt_allreduce_accum(agpt_ctx** ctxs, int n) { return agpt_reduce_accum(ctxs, n, -1); }
+
+// Fused reduce + CopyToSurface: GPU g sums ITS slice of the film over all accumulators (rank order, peer
+// loads) and packs it; the G slices go to the host over G PCIe links at once.  keep_sum != 0 also leaves
+// the summed film in ctxs[0]'s accumulator (slices written there by peer stores).
+int agpt_reduce_resolve(agpt_ctx** ctxs, int n, int samples, int keep_sum, uint32_t* host_rgb8) {
+	int rcode = CheckGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(samples > 0 && host_rgb8 != nullptr, AGPT_ERR_INVALID, "samples <= 0 or null output");
+	bool peers = n == 1;
+	if (n > 1) { rcode = EnablePeerAccess(ctxs, n, &peers); if (rcode != AGPT_OK) return rcode; }
+	if (!peers || (n > 1 && WantNccl())) {
+		// no peer memory between some pair: NCCL all-reduce, then the single-GPU resolve
+		rcode = agpt_reduce_accum(ctxs, n, -1);
+		if (rcode != AGPT_OK) return rcode;
+		return agpt_resolve(ctxs[0], samples, host_rgb8);
+	}
+	rcode = SyncGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	const size_t wh = (size_t)ctxs[0]->width * ctxs[0]->height;
+	PeerAccums pa;
+	pa.n = n;
+	for (int g = 0; g < n; g++) pa.p[g] = ctxs[g]->accum;
+	for (int g = 0; g < n; g++) {
+		agpt_ctx* c = ctxs[g];
+		int first, count;
+		SliceOf(g, n, wh, &first, &count);
+		CU(cudaSetDevice(c->device));
+		if (c->resolved.n != wh) CU(c->resolved.Alloc(wh));
+		CU(cudaEventRecord(c->evRender0, c->stream));
+		// (the sum may be written over ctxs[0]'s own addend: pixel i is read and written by this one thread only)
+		k_reduce_resolve<<<Blocks(count, 256), 256, 0, c->stream>>>(pa, first, count, (float)samples, keep_sum ? ctxs[0]->accum : nullptr, c->resolved.p);
+		CU(cudaGetLastError());
+		c->stats.kernel_launches++;
+		CU(cudaEventRecord(c->evRender1, c->stream));
+		CU(cudaMemcpyAsync(host_rgb8 + first, c->resolved.p + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	}
+	rcode = SyncGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	for (int g = 0; g < n; g++) {
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ctxs[g]->evRender0, ctxs[g]->evRender1);
+		ctxs[g]->stats.ms_reduce += ms; ctxs[g]->stats.reduce_path = 1;
+	}
+	return AGPT_OK;
+}
+
+// num_samples Tick bodies split over the group: context g renders first_sample + g, + g + n, ... (one host
+// thread per GPU: agpt_render paces its waves from the host).
+int agpt_render_multi(agpt_ctx** ctxs, int n, int first_sample, int num_samples, int max_depth, int rr_depth_arg, uint32_t flags) {
+	int rcode = CheckGroup(ctxs, n);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(num_samples >= 0, AGPT_ERR_INVALID, "bad sample range");
+	std::vector<int> rc((size_t)n, AGPT_OK);
+	std::vector<std::string> msg((size_t)n);
+	std::vector<std::thread> pool;
+	for (int g = 0; g < n; g++) {
+		int count = num_samples > g ? (num_samples - g + n - 1) / n : 0;
+		pool.emplace_back([=, &rc, &msg] {
+			if (count > 0) rc[g] = agpt_render(ctxs[g], first_sample + g, count, n, max_depth, rr_depth_arg, flags);
+			if (rc[g] != AGPT_OK) msg[g] = g_error;         // (thread-local message of the worker)
+		});
+	}
+	for (auto& t : pool) t.join();
+	for (int g = 0; g < n; g++) if (rc[g] != AGPT_OK) return Fail(rc[g], "GPU " + std::to_string(ctxs[g]->device) + ": " + msg[g]);
+	return AGPT_OK;
+}
+
+// ---- multi-process sharding (one rank per GPU: torchrun, MPI): peers' accumulators through CUDA IPC ----
+int agpt_accum_ipc_handle(agpt_ctx* c, void* handle64) {
+	NEED(c != nullptr && handle64 != nullptr, AGPT_ERR_INVALID, "null argument");
+	NEED(c->accum != nullptr && c->accum == c->accumOwn.p, AGPT_ERR_STATE, "the context must own its accumulator (agpt_set_film, no agpt_set_accum_dev)");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	CU(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, c->accumOwn.p));
+	memcpy(handle64, &h, sizeof(h));
+	return AGPT_OK;
+}
+
+int agpt_close_peer_accums(agpt_ctx* c) {
+	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	for (int r = 0; r < c->peerWorld; r++) if (r != c->peerRank && c->peerAccum[r]) cudaIpcCloseMemHandle(c->peerAccum[r]);
+	memset(c->peerAccum, 0, sizeof(c->peerAccum));
+	c->peerWorld = 0; c->peerRank = -1;
+	return AGPT_OK;
+}
+
+int agpt_open_peer_accums(agpt_ctx* c, int rank, int world, const void* handles64) {
+	NEED(c != nullptr && handles64 != nullptr && world >= 1 && world <= AGPT_MAX_PEERS && rank >= 0 && rank < world, AGPT_ERR_INVALID, "bad rank / world / handles");
+	NEED(c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	int rcode = agpt_close_peer_accums(c);
+	if (rcode != AGPT_OK) return rcode;
+	for (int r = 0; r < world; r++) {
+		if (r == rank) { c->peerAccum[r] = c->accum; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char*)handles64 + 64 * (size_t)r, sizeof(h));
+		void* p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { c->peerWorld = r; c->peerRank = rank; agpt_close_peer_accums(c); return Fail(AGPT_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e)); }
+		c->peerAccum[r] = (float4*)p;
+	}
+	c->peerRank = rank; c->peerWorld = world;
+	return AGPT_OK;
+}
+
+static int PeerTable(agpt_ctx* c, PeerAccums* pa) {
+	NEED(c != nullptr && c->peerWorld >= 1, AGPT_ERR_STATE, "peer accumulators not open (agpt_open_peer_accums)");
+	pa->n = c->peerWorld;
+	for (int r = 0; r < c->peerWorld; r++) pa->p[r] = c->peerAccum[r];
+	pa->p[c->peerRank] = c->accum;
+	return AGPT_OK;
+}
+
+// This rank's slice of the all-reduce.  The CALLER provides the two barriers: every rank has finished
+// rendering before any rank calls, and no rank reads its accumulator before every rank has returned.
+int agpt_allreduce_accum_peers(agpt_ctx* c) {
+	PeerAccums pa;
+	int rcode = PeerTable(c, &pa);
+	if (rcode != AGPT_OK) return rcode;
+	CU(cudaSetDevice(c->device));
+	int first, count;
+	SliceOf(c->peerRank, c->peerWorld, (size_t)c->width * c->height, &first, &count);
+	CU(cudaEventRecord(c->evRender0, c->stream));
+	k_allreduce_slice<<<Blocks(count, 256), 256, 0, c->stream>>>(pa, first, count);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaEventRecord(c->evRender1, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->evRender0, c->evRender1);
+	c->stats.ms_reduce += ms; c->stats.reduce_path = 1;
+	return AGPT_OK;
+}
+
+// The whole film on this rank (the root): sum of all ranks' accumulators in rank order -> packed pixels on the
+// host; keep_sum != 0 also stores the sum in this rank's accumulator.  Reads the peers, writes none of them:
+// only the barrier BEFORE the call is needed.
+int agpt_reduce_resolve_peers(agpt_ctx* c, int samples, int keep_sum, uint32_t* host_rgb8) {
+	PeerAccums pa;
+	int rcode = PeerTable(c, &pa);
+	if (rcode != AGPT_OK) return rcode;
+	NEED(samples > 0 && host_rgb8 != nullptr, AGPT_ERR_INVALID, "samples <= 0 or null output");
+	CU(cudaSetDevice(c->device));
+	const size_t wh = (size_t)c->width * c->height;
+	if (c->resolved.n != wh) CU(c->resolved.Alloc(wh));
+	CU(cudaEventRecord(c->evRender0, c->stream));
+	k_reduce_resolve<<<Blocks(wh, 256), 256, 0, c->stream>>>(pa, 0, (int)wh, (float)samples, keep_sum ? c->accum : nullptr, c->resolved.p);
+	CU(cudaGetLastError());
+	c->stats.kernel_launches++;
+	CU(cudaEventRecord(c->evRender1, c->stream));
+	CU(cudaMemcpyAsync(host_rgb8, c->resolved.p, wh * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->evRender0, c->evRender1);
+	c->stats.ms_reduce += ms; c->stats.reduce_path = 1;
+	return AGPT_OK;
 }
 
 // ---- pinned host memory for accumulators (fast H2D/D2H of the float4 film) --------------------

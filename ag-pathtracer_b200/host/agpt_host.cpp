@@ -197,6 +197,18 @@ int agpt_host_tracer_create(int max_depth, int device, agpt_host_tracer** out) {
 	return AGPT_OK;
 }
 
+int agpt_host_tracer_create_multi(int max_depth, const int* devices, int n, agpt_host_tracer** out) {
+	if (!out || !devices || n < 1) return HostFail("bad device list");
+	*out = nullptr;
+	g_hostError.clear();
+	HOST_TRY(
+		auto t = std::make_unique<agpt_host_tracer>();
+		t->tracer.reset(new CudaPathTracer(max_depth, std::vector<int>(devices, devices + n)));
+		*out = t.release();
+	)
+	return AGPT_OK;
+}
+
 int agpt_host_tracer_destroy(agpt_host_tracer* t) { delete t; return AGPT_OK; }
 
 int agpt_host_tracer_ctx(agpt_host_tracer* t, agpt_ctx** out) {
@@ -213,6 +225,18 @@ int agpt_host_tracer_render(agpt_host_tracer* t, agpt_host_scene* s, int width, 
 		if (reupload) t->tracer->Upload(s->scene);
 		Accumulator acc(width, height, reinterpret_cast<float3*>(host_rgba));     // the caller's film, in place
 		t->tracer->Render(s->scene, *s->camera, acc, first_sample, num_samples, depth_arg, flags);
+	)
+	return AGPT_OK;
+}
+
+int agpt_host_tracer_render_resolve(agpt_host_tracer* t, agpt_host_scene* s, int width, int height, float* host_rgba,
+		int samples_so_far, int first_sample, int num_samples, int depth_arg, uint32_t flags, uint32_t* host_rgb8) {
+	if (!t || !s || !host_rgba || !host_rgb8) return HostFail("null argument");
+	g_hostError.clear();
+	HOST_TRY(
+		Accumulator acc(width, height, reinterpret_cast<float3*>(host_rgba));
+		acc.SetNumSamples(samples_so_far);
+		t->tracer->RenderAndResolve(s->scene, *s->camera, acc, first_sample, num_samples, host_rgb8, depth_arg, flags);
 	)
 	return AGPT_OK;
 }

@@ -170,6 +170,8 @@ typedef struct agpt_stats {
 	float ms_trace_any;
 	float ms_shade;
 	float ms_other;            /* ms_render minus the three above (generate, accumulate, queue bookkeeping) */
+	float ms_reduce;           /* device time of this context's share of agpt_reduce_* / agpt_allreduce_* calls */
+	uint32_t reduce_path;      /* how the last one ran: 1 = this library's peer-memory kernels, 2 = ncclAllReduce */
 } agpt_stats;
 
 /* agpt_render / agpt_trace_* flags */
@@ -240,6 +242,38 @@ int agpt_read_accum(agpt_ctx* ctx, float* host_rgba);           /* D2H of float4
 int agpt_write_accum(agpt_ctx* ctx, const float* host_rgba);    /* H2D (resume) */
 /* Accumulator::CopyToSurface (myapp.h:34-41): /samples, pow(1/2.2), 8-bit pack 0x00RRGGBB. */
 int agpt_resolve(agpt_ctx* ctx, int samples, uint32_t* host_rgb8);
+
+/* ---- multi-GPU: sample-index sharding (north star "NCCL reduces the accumulators over NVLink") ----
+ * One context per GPU of ONE process, each holding the whole scene and a film of the same size.  GPU g of G
+ * renders the samples s = first + g (mod G) into its own accumulator (agpt_render with sample_stride = G, or
+ * agpt_render_multi, which runs the G renders on G host threads); the frame is the sum of the accumulators.
+ *
+ * agpt_reduce_accum sums them with this library's own kernel over NVLink peer memory -- each GPU owns a slice
+ * of the film, loads it from all accumulators, adds in RANK ORDER and stores the sum back to all (root = -1) or
+ * the root's GPU does it for the whole film (root >= 0: only ctxs[root] receives the sum).  Rank-order summation
+ * makes the result reproducible and equal to ((a0 + a1) + a2) + ... .  Where some pair of GPUs has no peer access,
+ * or with AGPT_REDUCE=nccl in the environment, it runs ncclAllReduce instead (libnccl is dlopen'ed on first use).
+ * agpt_allreduce_accum(ctxs, n) == agpt_reduce_accum(ctxs, n, -1).
+ *
+ * agpt_reduce_resolve is the fused end of a render: sum + Accumulator::CopyToSurface (myapp.h:34-41) in ONE
+ * kernel per GPU (its slice of the film), packed pixels straight to the host over all GPUs' PCIe links;
+ * keep_sum != 0 also leaves the summed film in ctxs[0]'s accumulator. */
+int agpt_render_multi(agpt_ctx** ctxs, int n, int first_sample, int num_samples, int max_depth, int rr_depth_arg, uint32_t flags);
+int agpt_reduce_accum(agpt_ctx** ctxs, int n, int root);
+int agpt_allreduce_accum(agpt_ctx** ctxs, int n);
+int agpt_reduce_resolve(agpt_ctx** ctxs, int n, int samples, int keep_sum, uint32_t* host_rgb8);
+
+/* The same exchange between PROCESSES (one rank per GPU: torchrun, MPI).  Each rank exports its context-owned
+ * accumulator as a 64-byte CUDA IPC handle; after the ranks have exchanged the handles (any transport), each
+ * opens the others' accumulators and the same peer-memory kernels run on them.  The caller provides the
+ * barriers: before either call every rank must have finished rendering; after agpt_allreduce_accum_peers no
+ * rank may touch its accumulator until every rank has returned.  agpt_reduce_resolve_peers runs on the root
+ * rank only and writes nothing to the peers. */
+int agpt_accum_ipc_handle(agpt_ctx* ctx, void* handle64);
+int agpt_open_peer_accums(agpt_ctx* ctx, int rank, int world, const void* handles64 /* world x 64 bytes, rank order */);
+int agpt_close_peer_accums(agpt_ctx* ctx);
+int agpt_allreduce_accum_peers(agpt_ctx* ctx);
+int agpt_reduce_resolve_peers(agpt_ctx* ctx, int samples, int keep_sum, uint32_t* host_rgb8);
 
 /* Page-locked host memory for accumulator buffers (what MALLOC64 is upstream, myapp.h:11):
  * agpt_read_accum / agpt_write_accum on such a buffer run at PCIe speed. */

@@ -69,6 +69,8 @@ int agpt_host_get_build_options(int* threads, char* cache_dir, int cache_dir_cap
 
 /* CudaPathTracer(max_depth, device) */
 int agpt_host_tracer_create(int max_depth, int device, agpt_host_tracer** out);
+/* CudaPathTracer(max_depth, {devices...}): renders split by sample index over the listed GPUs */
+int agpt_host_tracer_create_multi(int max_depth, const int* devices, int n, agpt_host_tracer** out);
 int agpt_host_tracer_destroy(agpt_host_tracer* tracer);
 int agpt_host_tracer_ctx(agpt_host_tracer* tracer, agpt_ctx** out);
 /* CudaPathTracer::Render(scene, Camera(scene.camera), Accumulator(width,height) over
@@ -76,6 +78,11 @@ int agpt_host_tracer_ctx(agpt_host_tracer* tracer, agpt_ctx** out);
  * reupload != 0 forces a fresh Scene::Flatten + upload inside the call. */
 int agpt_host_tracer_render(agpt_host_tracer* tracer, agpt_host_scene* scene, int width, int height,
 		float* host_rgba, int first_sample, int num_samples, int depth_arg, uint32_t flags, int reupload);
+/* CudaPathTracer::RenderAndResolve: Render, then Accumulator::CopyToSurface of the film (which holds
+ * samples_so_far samples per pixel before the call) into host_rgb8[y*W + x] = 0x00RRGGBB -- the sum over
+ * GPUs and the display transform fused in one kernel per GPU. */
+int agpt_host_tracer_render_resolve(agpt_host_tracer* tracer, agpt_host_scene* scene, int width, int height, float* host_rgba,
+		int samples_so_far, int first_sample, int num_samples, int depth_arg, uint32_t flags, uint32_t* host_rgb8);
 /* CudaPathTracer::Li(Ray(o, d), scene, depth_arg) */
 int agpt_host_tracer_li(agpt_host_tracer* tracer, agpt_host_scene* scene, const float* o3, const float* d3, int depth_arg, float* out3);
 
