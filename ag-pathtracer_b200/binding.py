@@ -73,7 +73,7 @@ class RawMesh:
 
 class Stats(ctypes.Structure):  # agpt_stats
     _fields_ = [(n, c_uint64) for n in ("paths", "rays_closest", "rays_shadow", "rays_mis", "rays_skip", "rays_mis_culled", "rays_tail_culled")] + \
-               [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests")] + \
+               [(n, c_uint64 * 2) for n in ("node_visits", "box_tests", "tri_tests", "analytic_tests", "warp_steps", "lane_steps")] + \
                [(n, c_uint64) for n in ("kernel_launches", "launches_closest", "launches_any", "launches_shade", "waves")] + \
                [(n, c_float) for n in ("ms_render", "ms_trace_closest", "ms_trace_any", "ms_shade", "ms_other", "ms_reduce")] + \
                [("reduce_path", c_uint32)]
@@ -298,6 +298,19 @@ class Context:
         _check(core().agpt_reduce_resolve_peers(self._h, c_int(samples), c_int(1 if keep_sum else 0), out.ctypes.data_as(POINTER(c_uint32))))
         return out
 
+    def wave_stats(self, kind=0, max_waves=64):
+        """Per-wave (= per-bounce) traversal counters of the COUNTERS renders since reset_stats: list of dicts."""
+        rows = (c_uint64 * (8 * max_waves))()
+        n = c_int(0)
+        _check(core().agpt_get_wave_stats(self._h, c_int(kind), rows, c_int(max_waves), byref(n)))
+        names = ("rays", "node_visits", "box_tests", "tri_tests", "analytic_tests", "warp_steps", "lane_steps")
+        return [dict(zip(names, [int(rows[8 * w + k]) for k in range(7)])) for w in range(n.value)]
+
+    def probe_bandwidth(self, nbytes, iters):
+        g = c_float(0)
+        _check(core().agpt_probe_bandwidth(self._h, ctypes.c_size_t(nbytes), c_int(iters), byref(g)))
+        return g.value
+
     def debug_status(self):
         out = (c_uint64 * 4)()
         _check(core().agpt_debug_status(self._h, out))
@@ -501,6 +514,16 @@ class HostTracer:
         _check(host().agpt_host_tracer_render(self._h, scene.handle, c_int(width), c_int(height), _fptr(accum), c_int(first_sample),
                                               c_int(num_samples), c_int(depth_arg), c_uint32(flags), c_int(1 if reupload else 0)), host_side=True)
         return accum
+
+    def stats(self, reset=False):
+        """agpt_stats of the tracer's first context (CudaPathTracer::Context())."""
+        ctx = c_void_p()
+        _check(host().agpt_host_tracer_ctx(self._h, byref(ctx)), host_side=True)
+        s = Stats()
+        _check(core().agpt_get_stats(ctx, byref(s)))
+        if reset:
+            _check(core().agpt_reset_stats(ctx))
+        return s
 
     def render_resolve(self, scene, width, height, accum, samples_so_far, first_sample, num_samples, depth_arg=0, flags=0):
         """RenderAndResolve: returns the packed 0x00RRGGBB image of the film after these samples."""

@@ -109,7 +109,7 @@ struct agpt_ctx {
 	DevBuf<int> hist;             // AGPT_BUCKETS x { histogram, offsets, running }
 	DevBuf<int> counts;           // 2 x 3
 	DevBuf<int> survivors, survivorCount;   // paths k_shade_b works on this wave
-	DevBuf<unsigned long long> traceCounters;   // 4 closest + 4 any-hit
+	DevBuf<unsigned long long> traceCounters;   // [2][8] totals (closest-hit, any-hit), then [2][AGPT_MAX_WAVE_ROWS][8] per wave (FlushCounters)
 	DevBuf<RayCounters> rayCounters;
 	int* hostCounts = nullptr;    // pinned ring of kRing x 3 ints
 	cudaEvent_t ringEvents[8] = {};
@@ -261,13 +261,13 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // ---- launch helpers: template flags from run-time flags --------------------------------------
-static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt) {
-	if (count) { if (strictBoxes) k_trace_closest<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
-	else { if (strictBoxes) k_trace_closest<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_closest<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
+	if (count) { if (strictBoxes) k_trace_closest<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_closest<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
+	else { if (strictBoxes) k_trace_closest<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_closest<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
 }
-static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt) {
-	if (count) { if (strictBoxes) k_trace_any<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
-	else { if (strictBoxes) k_trace_any<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); else k_trace_any<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt); }
+static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
+	if (count) { if (strictBoxes) k_trace_any<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_any<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
+	else { if (strictBoxes) k_trace_any<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_any<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
 }
 template <bool ANY>
 static void LaunchTable(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const float4* o, const float4* d, int n, agpt_hit* out, unsigned long long* cnt) {
@@ -314,7 +314,7 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(c->counts.Alloc(6));
 	CU(c->survivorCount.Alloc(1));
 	CU(c->hist.Alloc(3 * AGPT_BUCKETS));
-	CU(c->traceCounters.Alloc(8));
+	CU(c->traceCounters.Alloc(2 * AGPT_WAVE_COUNTERS * (1 + AGPT_MAX_WAVE_ROWS)));
 	CU(c->rayCounters.Alloc(1));
 	CU(cudaMemset(c->traceCounters.p, 0, c->traceCounters.Bytes()));
 	CU(cudaMemset(c->rayCounters.p, 0, c->rayCounters.Bytes()));
@@ -651,7 +651,8 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 	const bool overlap = c->overlapAny && !timing;
 	float msClosest = 0, msAny = 0, msShade = 0;
 	unsigned long long* cntClosest = c->traceCounters.p;
-	unsigned long long* cntAny = c->traceCounters.p + 4;
+	unsigned long long* cntAny = c->traceCounters.p + AGPT_WAVE_COUNTERS;
+	unsigned long long* waveRows = c->traceCounters.p + 2 * AGPT_WAVE_COUNTERS;      // [kind][wave][8]
 
 	int ubClosest = n, ubShadow = 0, ubActive = n;   // upper bounds of the current wave's queue lengths
 	int cur = 0, wave = 0;
@@ -690,7 +691,8 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
 		if (fork) CU(cudaEventRecord(c->evFork, c->stream));
 		if (ubClosest > 0) {
-			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest);
+			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest,
+				waveRows + (size_t)AGPT_WAVE_COUNTERS * (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1));
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
 		if (wave == 0 && bucketing && !c->gridCalibrated && c->calibrateGrid && n >= 4096) {
@@ -702,12 +704,14 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (fork) {
 			CU(cudaStreamWaitEvent(c->sideStream, c->evFork, 0));
-			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->sideStream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny);
+			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->sideStream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
+				waveRows + (size_t)AGPT_WAVE_COUNTERS * (AGPT_MAX_WAVE_ROWS + (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1)));
 			c->stats.kernel_launches++; c->stats.launches_any++;
 			CU(cudaEventRecord(c->evJoin, c->sideStream));
 			CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
 		} else if (ubShadow > 0) {
-			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny);
+			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
+				waveRows + (size_t)AGPT_WAVE_COUNTERS * (AGPT_MAX_WAVE_ROWS + (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1)));
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
@@ -826,7 +830,7 @@ static int TraceTable(agpt_ctx* c, const DScene& sc, const float4* rayO, const f
 	CU(out.Alloc(n));
 	const bool count = flags & AGPT_FLAG_COUNTERS, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
 	int blocks = Blocks(n, AGPT_TRACE_THREADS);
-	if (any_hit) LaunchTable<true>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p + 4);
+	if (any_hit) LaunchTable<true>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p + AGPT_WAVE_COUNTERS);
 	else LaunchTable<false>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
@@ -1231,18 +1235,60 @@ int agpt_get_stats(agpt_ctx* c, agpt_stats* out) {
 	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
 	CU(cudaSetDevice(c->device));
 	CU(cudaStreamSynchronize(c->stream));
-	unsigned long long tc[8];
+	unsigned long long tc[2 * AGPT_WAVE_COUNTERS];
 	RayCounters rc;
 	CU(cudaMemcpy(tc, c->traceCounters.p, sizeof(tc), cudaMemcpyDeviceToHost));
 	CU(cudaMemcpy(&rc, c->rayCounters.p, sizeof(rc), cudaMemcpyDeviceToHost));
 	*out = c->stats;
 	for (int k = 0; k < 2; k++) {
-		out->node_visits[k] = tc[4 * k]; out->box_tests[k] = tc[4 * k + 1]; out->tri_tests[k] = tc[4 * k + 2]; out->analytic_tests[k] = tc[4 * k + 3];
+		const unsigned long long* t = tc + AGPT_WAVE_COUNTERS * k;
+		out->node_visits[k] = t[1]; out->box_tests[k] = t[2]; out->tri_tests[k] = t[3]; out->analytic_tests[k] = t[4];
+		out->warp_steps[k] = t[5]; out->lane_steps[k] = t[6];
 	}
 	out->rays_closest += rc.rays_closest; out->rays_shadow = rc.rays_shadow; out->rays_mis = rc.rays_mis; out->rays_skip = rc.rays_skip; out->rays_mis_culled = rc.rays_mis_culled; out->rays_tail_culled = rc.rays_tail_culled;
 	out->ms_other = out->ms_render - out->ms_trace_closest - out->ms_trace_any - out->ms_shade;
 	return AGPT_OK;
 }
+int agpt_get_wave_stats(agpt_ctx* c, int kind, agpt_wave_stats* out, int max_waves, int* n_waves) {
+	NEED(c != nullptr && out != nullptr && n_waves != nullptr && (kind == 0 || kind == 1) && max_waves >= 1, AGPT_ERR_INVALID, "bad argument");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	std::vector<unsigned long long> rows((size_t)AGPT_MAX_WAVE_ROWS * AGPT_WAVE_COUNTERS);
+	CU(cudaMemcpy(rows.data(), c->traceCounters.p + 2 * AGPT_WAVE_COUNTERS + (size_t)kind * AGPT_MAX_WAVE_ROWS * AGPT_WAVE_COUNTERS, rows.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	int n = 0;
+	for (int w = 0; w < AGPT_MAX_WAVE_ROWS && w < max_waves; w++) {
+		const unsigned long long* r = &rows[(size_t)w * AGPT_WAVE_COUNTERS];
+		out[w].rays = r[0]; out[w].node_visits = r[1]; out[w].box_tests = r[2]; out[w].tri_tests = r[3]; out[w].analytic_tests = r[4];
+		out[w].warp_steps = r[5]; out[w].lane_steps = r[6]; out[w].reserved = 0;
+		if (r[0]) n = w + 1;
+	}
+	*n_waves = n;
+	return AGPT_OK;
+}
+
+int agpt_probe_bandwidth(agpt_ctx* c, size_t bytes, int iters, float* gbs_out) {
+	NEED(c != nullptr && gbs_out != nullptr && bytes >= 4096 && iters >= 1, AGPT_ERR_INVALID, "bad probe arguments");
+	CU(cudaSetDevice(c->device));
+	DevBuf<uint4> buf;
+	DevBuf<unsigned> sink;
+	const size_t n16 = bytes / 16;
+	CU(buf.Alloc(n16)); CU(sink.Alloc(1));
+	CU(cudaMemsetAsync(buf.p, 0, n16 * 16, c->stream));
+	const int blocks = c->smCount * 4;
+	k_probe_bandwidth<<<blocks, 512, 0, c->stream>>>(buf.p, n16, 1, sink.p);          // warm-up: page in, fill L2
+	CU(cudaEventRecord(c->evA, c->stream));
+	k_probe_bandwidth<<<blocks, 512, 0, c->stream>>>(buf.p, n16, iters, sink.p);
+	CU(cudaEventRecord(c->evB, c->stream));
+	CU(cudaGetLastError());
+	c->stats.kernel_launches += 2;
+	CU(cudaStreamSynchronize(c->stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->evA, c->evB);
+	*gbs_out = ms > 0 ? (float)((double)n16 * 16 * iters / (ms * 1e-3) / 1e9) : 0.f;
+	buf.Free(); sink.Free();
+	return AGPT_OK;
+}
+
 int agpt_debug_status(agpt_ctx* c, uint64_t* out4) {
 	NEED(c != nullptr && out4 != nullptr, AGPT_ERR_INVALID, "null argument");
 	out4[0] = out4[1] = out4[2] = out4[3] = 0;

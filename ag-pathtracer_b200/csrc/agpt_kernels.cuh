@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 // ---- trace kernels ---------------------------------------------------------------------
 template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
-		unsigned long long* counters) {
+		unsigned long long* counters, unsigned long long* waveRow) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	TraceCounters cnt = { 0, 0, 0, 0 };
+	TraceCounters cnt = { 0, 0, 0, 0, 0, 0 };
 	// The queue length lives on the device (the host launches an upper bound of blocks).  The
 	// entry is fetched unconditionally -- queues are allocated with slack past any launchable
 	// index -- so that the two loads overlap instead of costing two dependent round trips.
@@ -299,15 +299,15 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 		}
 		else ps.misPrim[path] = hit.prim;
 	}
-	if (COUNT) FlushCounters(cnt, counters);
+	if (COUNT) FlushCounters(cnt, lane, counters, waveRow);
 }
 
 template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
-		unsigned long long* counters) {
+		unsigned long long* counters, unsigned long long* waveRow) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	TraceCounters cnt = { 0, 0, 0, 0 };
+	TraceCounters cnt = { 0, 0, 0, 0, 0, 0 };
 	int path = queue[i];
 	const int count = *countPtr;
 	bool lane = i < count;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 	HitRecord hit;
 	bool occluded = TraceScene<true, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) ps.shadowOccluded[path] = occluded ? 1 : 0;
-	if (COUNT) FlushCounters(cnt, counters);
+	if (COUNT) FlushCounters(cnt, lane, counters, waveRow);
 }
 
 // Standalone rays (agpt_trace_rays / agpt_trace_primary): hit table out.
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 		int count, agpt_hit* out, unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	TraceCounters cnt = { 0, 0, 0, 0 };
+	TraceCounters cnt = { 0, 0, 0, 0, 0, 0 };
 	bool lane = i < count;
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = rayO[i]; d = rayD[i]; }
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 		h.t = (found && !ANY) ? hit.t : 0.f;
 		out[i] = h;
 	}
-	if (COUNT) FlushCounters(cnt, counters);
+	if (COUNT) FlushCounters(cnt, lane, counters, nullptr);
 }
 
 // ---- shade -------------------------------------------------------------------------------
@@ -813,6 +813,21 @@ __global__ void __launch_bounds__(256) k_resolve(const float4* __restrict__ accu
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	out[i] = ResolvePixel(accum[i], samples);
+}
+
+// ---- bandwidth probe: what a plain streaming read of this library's own making reaches on this GPU ----
+// `n16` 16-byte words read `iters` times by a persistent grid with 128-bit loads.  A buffer that fits in L2
+// measures L2 bandwidth (the roofline denominator for the trace kernels' L2 traffic), one far larger than L2
+// measures HBM read bandwidth.
+__global__ void __launch_bounds__(512) k_probe_bandwidth(const uint4* __restrict__ data, size_t n16, int iters, unsigned* sink) {
+	unsigned acc = 0;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int it = 0; it < iters; it++)
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+			uint4 v = __ldcg(data + i);        // cached in L2 only: a second pass must not be served from L1
+			acc ^= v.x ^ v.y ^ v.z ^ v.w;
+		}
+	if (acc == 0x9e3779b9u) sink[0] = acc;      // (never true for the zero-filled buffer: keeps the loads alive)
 }
 
 // ---- upload-time pass: flag triangles upstream would reject as degenerate (trianglemesh.cpp:71-77)

@@ -32,6 +32,7 @@
 
 struct TraceCounters {
 	unsigned long long node_visits, box_tests, tri_tests, analytic_tests;
+	unsigned long long warp_steps, lane_steps;     // trips of the lockstep walk (counted by lane 0) and lanes with work in them: lane_steps / warp_steps = rays alive per step
 };
 
 struct HitRecord {
@@ -134,6 +135,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 	int sp = 0;
 	bool active = lane;
 	while (__any_sync(0xffffffffu, active && (inside || cand != 0u))) {
+		if (COUNT) { if ((threadIdx.x & 31) == 0) cnt.warp_steps++; if (active && (inside || cand != 0u)) cnt.lane_steps++; }
 		if (active && (inside || cand != 0u)) {
 			if (!inside) {
 				// enter the next candidate mesh
@@ -319,14 +321,18 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 	return found;
 }
 
-// Warp-aggregated flush of per-thread counters: one atomic per counter per warp.
-__device__ __forceinline__ void FlushCounters(const TraceCounters& c, unsigned long long* global4) {
-	unsigned long long v[4] = { c.node_visits, c.box_tests, c.tri_tests, c.analytic_tests };
+// Warp-aggregated flush of per-thread counters: one atomic per counter per warp.  `totals` = 8 counters of
+// the kernel class (agpt_stats), `waveRow` = the same 8 for the current wave (agpt_get_wave_stats) or nullptr:
+// rays, node visits, box tests, triangle tests, analytic records, warp steps, lane steps, -.
+#define AGPT_WAVE_COUNTERS 8
+#define AGPT_MAX_WAVE_ROWS 64
+__device__ __forceinline__ void FlushCounters(const TraceCounters& c, bool hasRay, unsigned long long* totals, unsigned long long* waveRow) {
+	unsigned long long v[7] = { hasRay ? 1ull : 0ull, c.node_visits, c.box_tests, c.tri_tests, c.analytic_tests, c.warp_steps, c.lane_steps };
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
+	for (int k = 0; k < 7; k++) {
 		unsigned long long x = v[k];
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-		if ((threadIdx.x & 31) == 0 && x) atomicAdd(global4 + k, x);
+		if ((threadIdx.x & 31) == 0 && x) { atomicAdd(totals + k, x); if (waveRow) atomicAdd(waveRow + k, x); }
 	}
 }

@@ -160,6 +160,8 @@ typedef struct agpt_stats {
 	uint64_t box_tests[2];
 	uint64_t tri_tests[2];     /* triangles fetched and tested (48 B each) */
 	uint64_t analytic_tests[2];/* sphere / plane records tested (32 B each) */
+	uint64_t warp_steps[2];    /* trips of the lockstep BVH walk, counted once per warp */
+	uint64_t lane_steps[2];    /* lanes that had work in those trips: lane_steps / warp_steps = rays alive per step (of 32) */
 	uint64_t kernel_launches;  /* launches of this library's kernels since agpt_reset_stats */
 	uint64_t launches_closest; /* of which closest-hit trace, any-hit trace, shade */
 	uint64_t launches_any;
@@ -282,6 +284,17 @@ int agpt_host_free(void* p);
 
 /* ---- observability ------------------------------------------------------------------- */
 
+/* Traversal work per WAVE of the renders made with AGPT_FLAG_COUNTERS since agpt_reset_stats.  Wave w of a batch
+ * traces the path rays of bounce w (and the shadow / MIS rays of the vertex before it), so this is the per-bounce
+ * N_int / N_tri / divergence report of SURVEY 8d (RecursiveHit, bvhtrimesh.h:332-384).  kind 0 = closest-hit kernel
+ * (path + MIS rays), 1 = any-hit kernel (shadow rays).  Fills up to max_waves rows; *n_waves = rows in use. */
+typedef struct agpt_wave_stats {
+	uint64_t rays, node_visits, box_tests, tri_tests, analytic_tests, warp_steps, lane_steps, reserved;
+} agpt_wave_stats;
+int agpt_get_wave_stats(agpt_ctx* ctx, int kind, agpt_wave_stats* out, int max_waves, int* n_waves);
+/* Read bandwidth (GB/s) a plain streaming kernel of this library reaches on this GPU over `bytes` of device memory
+ * read `iters` times: bytes well inside the L2 size measures L2, bytes far beyond it HBM (roofline denominators). */
+int agpt_probe_bandwidth(agpt_ctx* ctx, size_t bytes, int iters, float* gbs_out);
 int agpt_get_stats(agpt_ctx* ctx, agpt_stats* out);
 int agpt_reset_stats(agpt_ctx* ctx);
 /* Builds with -DAGPT_DEBUG (libagpt_debug.so) check stack depth, node / triangle / primitive indices and queue

@@ -1,4 +1,8 @@
-"""Short single-GPU workload for ncu captures (not a test): one render call, no counters."""
+"""Short single-GPU workload for ncu captures (not a test): one agpt_render call of a configuration --
+with `16` samples per pixel on cfg 3 this is exactly one bench.py step.  Also writes the ray counts of the
+kernel classes beside the capture (gpurun_out/ncu_target_stats.json), for profiles/ncu_step_summary.py."""
+import json
+import os
 import sys
 sys.path.insert(0, '.')
 from tests.conftest import load_agpt
@@ -9,3 +13,8 @@ hs = agpt.HostScene(cfg, level); ctx = agpt.Context(0); hs.upload(ctx)
 ctx.set_film(d['width'], d['height'])
 ctx.render(0, spp, d['max_depth'], d['depth_arg'], flags)
 s = ctx.stats(); print('ms', s.ms_render, 'Mrays/s', s.rays / s.ms_render / 1e3)
+os.makedirs('gpurun_out', exist_ok=True)
+json.dump({"config": cfg, "level": level, "spp": spp, "width": d['width'], "height": d['height'], "paths": s.paths,
+           "rays_closest_kernel": s.rays_closest + s.rays_mis, "rays_any_kernel": s.rays_shadow, "waves": s.waves,
+           "launches_closest": s.launches_closest, "launches_any": s.launches_any, "launches_shade": s.launches_shade, "ms_render": s.ms_render},
+          open('gpurun_out/ncu_target_stats.json', 'w'))

@@ -34,7 +34,7 @@ def test_host_exports_every_declared_symbol(agpt):
 def test_struct_layouts(agpt):
     assert ctypes.sizeof(agpt.Material) == 64
     assert agpt.HIT_DTYPE.itemsize == 16
-    assert ctypes.sizeof(agpt.Stats) == 7 * 8 + 4 * 16 + 5 * 8 + 6 * 4 + 4 + 4     # + reduce_path, trailing pad to 8
+    assert ctypes.sizeof(agpt.Stats) == 7 * 8 + 6 * 16 + 5 * 8 + 6 * 4 + 4 + 4     # + reduce_path, trailing pad to 8
 
 
 def test_no_cpu_fallback(agpt):
