@@ -242,7 +242,7 @@ __device__ __forceinline__ void TriangleSurface(const DMesh& mesh, int slot, flo
 // ---------------------------------------------------------------------------------------
 // Sphere light sampling (intersectable.h:230-317)
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void SphereSampleFrom(const agpt_sphere& sp, float3 refP, float2 u, float3* pOut, float3* nOut, float* pdf) {
+__device__ __forceinline__ void SphereSampleFrom(const agpt_sphere& sp, float3 refP, float2 u, float3* pOut, float3* nOut, float* pdf) {
 	float3 pCenter = f3(sp.center);
 	if (sqrLength(refP - pCenter) <= sp.r2) {
 		// uniform area sampling (:230-237) converted to solid angle (:245-256)
@@ -395,7 +395,7 @@ struct LobeEval {
 	float pdfCos;      // BxDF::Pdf of a cosine-sampled lobe (reflection.h:16-18)
 	float pdfMicro;    // MicrofacetReflection::Pdf (reflection.h:67-71)
 };
-__device__ __noinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEval& out) {
+__device__ __forceinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEval& out) {
 	const agpt_material& m = *v.b.mat;
 	const float absCosI = AbsCosTheta(wi);
 	const bool same = SameHemisphere(v.wo, wi);
@@ -453,7 +453,7 @@ struct DirSample {
 	bool ok;          // false where BSDF::Sample_f returns black (reflection.h:130-157)
 };
 // First half of BSDF::Sample_f: choose the lobe, remap u, sample its direction (reflection.h:126-157).
-__device__ __noinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, bool skipSpecular, DirSample& s) {
+__device__ __forceinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, bool skipSpecular, DirSample& s) {
 	const agpt_material& m = *v.b.mat;
 	int lobes[4];
 	int matching = LobeList(m, skipSpecular, lobes);

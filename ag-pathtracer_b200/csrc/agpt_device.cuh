@@ -150,7 +150,9 @@ __device__ __forceinline__ float GlibcSinCos(float y, bool cosine) {
 }
 __device__ __noinline__ float rsin(float x) { return GlibcSinCos(x, false); }
 __device__ __noinline__ float rcos(float x) { return GlibcSinCos(x, true); }
-__device__ __noinline__ void rsincos(float x, float* s, float* c) { *s = GlibcSinCos(x, false); *c = GlibcSinCos(x, true); }
+// (returned by value: out-pointers of an out-of-line function live in local memory)
+__device__ __noinline__ float2 rsincos2(float x) { return make_float2(GlibcSinCos(x, false), GlibcSinCos(x, true)); }
+__device__ __forceinline__ void rsincos(float x, float* s, float* c) { float2 sc = rsincos2(x); *s = sc.x; *c = sc.y; }
 __device__ __noinline__ float racos(float x) {
 	const float one = 1.0000000000e+00f, pi = 3.1415925026e+00f, pio2_hi = 1.5707962513e+00f, pio2_lo = 7.5497894159e-08f,
 		pS0 = 1.6666667163e-01f, pS1 = -3.2556581497e-01f, pS2 = 2.0121252537e-01f, pS3 = -4.0055535734e-02f,

@@ -572,7 +572,20 @@ def main():
             def orender(first, flags=0):
                 pkg.multigpu.render_sharded(octx, first, total_spp, od["max_depth"], od["depth_arg"], me, nranks, flags)
 
-            orender(0)                                          # warm-up
+            def end_of_frame(samples):
+                # sum of the accumulators (N > 1) + CopyToSurface, pixels on the root's host
+                if multi:
+                    if oroute.startswith("peer"):
+                        dist.barrier()
+                        out = octx.reduce_resolve_peers(samples) if rank == 0 else None
+                        dist.barrier()
+                        return out
+                    dist.all_reduce(oacc, op=dist.ReduceOp.SUM)
+                    return octx.resolve(samples) if rank == 0 else None
+                return octx.resolve(samples)
+
+            orender(0)                                          # warm-up of the render and of the end of frame
+            end_of_frame(total_spp)
             octx.clear(); octx.reset_stats()
             torch.cuda.synchronize()
             if multi:
@@ -583,20 +596,7 @@ def main():
             for k in range(reps):
                 orender((1 + k) * total_spp)
             e1.record(stream)
-            rgb = None
-            if multi:
-                # strong scaling's end of frame: sum of the accumulators + CopyToSurface, pixels on the root's host
-                if oroute.startswith("peer"):
-                    dist.barrier()
-                    if rank == 0:
-                        rgb = octx.reduce_resolve_peers(reps * total_spp)
-                    dist.barrier()
-                else:
-                    dist.all_reduce(oacc, op=dist.ReduceOp.SUM)
-                    if rank == 0:
-                        rgb = octx.resolve(reps * total_spp)
-            else:
-                rgb = octx.resolve(reps * total_spp)
+            rgb = end_of_frame(reps * total_spp)
             e2.record(stream)
             torch.cuda.synchronize()
             ost = octx.stats()
@@ -608,8 +608,9 @@ def main():
             orays, opaths = [float(x) for x in s.tolist()]
             entry = {"workload": od["name"], "width": od["width"], "height": od["height"], "max_depth": od["max_depth"], "triangles": osc.counts()["tris"],
                      "scaling": "strong" if multi else "single GPU", "n_gpus": nranks, "total_spp_per_frame": total_spp, "frames": reps,
-                     "ms_per_frame": oms / reps, "Mrays_per_s": orays / oms / 1e3, "spp_per_s": opaths / (od["width"] * od["height"]) / (oms * 1e-3),
-                     "rays_per_path": orays / max(opaths, 1), "end_of_frame_ms": oms_end,
+                     "ms_render_per_frame": (oms - oms_end) / reps, "end_of_frame_ms": oms_end, "ms_timed_region": oms,
+                     "Mrays_per_s": orays / oms / 1e3, "spp_per_s": opaths / (od["width"] * od["height"]) / (oms * 1e-3),
+                     "rays_per_path": orays / max(opaths, 1),
                      "end_of_frame": ("accumulator sum + resolve over " + oroute) if multi else "resolve",
                      "host_bvh_build_s": build_s, "scene_bytes": osc.counts()["bytes"]}
             if rank == 0 and oc == 5:
