@@ -39,7 +39,7 @@ def main(csv_path, stats_path, out_path):
     names = {}
     for r in rows:
         lid = int(r["ID"])
-        names[lid] = re.sub(r"<.*", "", r["Kernel Name"].split("(")[0]).strip()
+        names[lid] = re.sub(r"<.*", "", r["Kernel Name"].split("(")[0]).replace("void ", "").strip()
         per_launch[lid][r["Metric Name"]] = to_float(r["Metric Value"], r["Metric Unit"])
     agg = defaultdict(lambda: defaultdict(float))
     for lid, m in per_launch.items():
