@@ -20,6 +20,7 @@ FLAG_COUNTERS = 1
 FLAG_TIMING = 2
 FLAG_STRICT_BOXES = 4
 FLAG_RAYS_FINAL = 8
+FLAG_RR_BY_BOUNCE = 16
 
 MAT_DISNEY = 1
 MAT_MIRROR = 2
@@ -49,7 +50,7 @@ SPHERE_DTYPE = np.dtype([("center", np.float32, 3), ("r", np.float32), ("r2", np
 PLANE_DTYPE = np.dtype([("o", np.float32, 3), ("half_x", np.float32), ("half_z", np.float32), ("pad", np.float32, 3)])     # agpt_plane
 LIGHT_DTYPE = np.dtype([("type", np.int32), ("prim", np.int32), ("pad", np.float32, 2), ("lemit", np.float32, 3), ("pad2", np.float32)])   # agpt_light
 NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("first", np.int32), ("count", np.int32)])        # agpt_bvh_node
-PRIM_SPHERE, PRIM_PLANE, PRIM_BVH_MESH, PRIM_MESH = 0, 1, 2, 3
+PRIM_SPHERE, PRIM_PLANE, PRIM_BVH_MESH, PRIM_MESH, PRIM_INSTANCE = 0, 1, 2, 3, 4
 LIGHT_AREA, LIGHT_UNIFORM_INFINITE, LIGHT_INFINITE_AREA = 0, 1, 2
 
 
@@ -200,6 +201,12 @@ class Context:
         rows = np.ascontiguousarray(rows, dt)
         _check(fn(self._h, rows.ctypes.data_as(c_void_p), c_int(len(rows))))
 
+    def upload_instances(self, rows):
+        """rows: structured array of agpt_instance records (mesh, pad[3], object_to_world[12], world_to_object[12])."""
+        rows = np.ascontiguousarray(rows)
+        assert rows.dtype.itemsize == 112
+        _check(core().agpt_upload_instances(self._h, rows.ctypes.data_as(c_void_p), c_int(len(rows))))
+
     def set_camera(self, cam19):
         cam19 = np.ascontiguousarray(cam19, np.float32)
         assert cam19.size == 19
@@ -252,11 +259,11 @@ class Context:
                                       c_uint32(flags), out.ctypes.data_as(c_void_p)))
         return out
 
-    def li_pixels(self, xs, ys, ss, max_depth, depth_arg=0):
+    def li_pixels(self, xs, ys, ss, max_depth, depth_arg=0, flags=0):
         xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); ss = np.ascontiguousarray(ss, np.int32)
         out = np.empty((len(xs), 3), np.float32)
         ip = lambda a: a.ctypes.data_as(POINTER(c_int))
-        _check(core().agpt_li_pixels(self._h, c_int(len(xs)), ip(xs), ip(ys), ip(ss), c_int(max_depth), c_int(depth_arg), _fptr(out)))
+        _check(core().agpt_li_pixels(self._h, c_int(len(xs)), ip(xs), ip(ys), ip(ss), c_int(max_depth), c_int(depth_arg), c_uint32(flags), _fptr(out)))
         return out
 
     def li_rays(self, rays7, rng_states, max_depth, depth_arg=0, flags=0):
@@ -458,7 +465,7 @@ class HostScene:
 
     def tables(self):
         """agpt_scene_tables view (opaque bytes) of the flattened scene, valid while the scene lives."""
-        buf = ctypes.create_string_buffer(6 * 16 + 19 * 4 + 4 + 40 + 16)
+        buf = ctypes.create_string_buffer(256)       # sizeof(agpt_scene_tables) = 232
         _check(host().agpt_host_scene_tables(self._h, buf), host_side=True)
         return buf
 

@@ -70,6 +70,9 @@ struct agpt_ctx {
 	DevBuf<agpt_sphere> spheres;
 	DevBuf<agpt_plane> planes;
 	DevBuf<agpt_prim> prims;
+	DevBuf<agpt_instance> instances;     // extension: placed meshes
+	std::vector<agpt_instance> hostInstances;
+	int nInstances = 0;
 	DevBuf<int> sphereRun;
 	DevBuf<float4> sphereRunBox;
 	std::vector<agpt_sphere> hostSpheres;
@@ -177,7 +180,7 @@ static void SetBucketGrid(DScene& s, const float* lo, const float* hi) {
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
-	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.sphereRunBox = c->sphereRunBox.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p;
+	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.sphereRunBox = c->sphereRunBox.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p; s.instances = c->instances.p;
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
 	s.envRgb = c->envRgb.p; s.envFunc = c->envFunc.p; s.envCdf = c->envCdf.p; s.envFuncInt = c->envFuncInt; s.envW = c->envW; s.envH = c->envH;
@@ -226,11 +229,13 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 	// table consistency: every row must point inside its table
 	for (size_t i = 0; i < c->hostPrims.size(); i++) {
 		const agpt_prim& p = c->hostPrims[i];
-		int limit = p.type == AGPT_PRIM_SPHERE ? c->nSpheres : p.type == AGPT_PRIM_PLANE ? c->nPlanes : c->nMeshes;
-		NEED(p.type >= 0 && p.type <= 3 && p.payload >= 0 && p.payload < limit, AGPT_ERR_INVALID, "primitive row points outside its shape table");
+		int limit = p.type == AGPT_PRIM_SPHERE ? c->nSpheres : p.type == AGPT_PRIM_PLANE ? c->nPlanes : p.type == AGPT_PRIM_INSTANCE ? c->nInstances : c->nMeshes;
+		NEED(p.type >= 0 && p.type <= 4 && p.payload >= 0 && p.payload < limit, AGPT_ERR_INVALID, "primitive row points outside its shape table");
 		NEED(p.material < c->nMats, AGPT_ERR_INVALID, "primitive row points outside the material table");
 		NEED(p.area_light < (int)c->hostLights.size(), AGPT_ERR_INVALID, "primitive row points outside the light table");
 	}
+	for (auto& in : c->hostInstances)
+		NEED(in.mesh >= 0 && in.mesh < c->nMeshes, AGPT_ERR_INVALID, "instance row points outside the mesh table");
 	for (auto& l : c->hostLights)
 		NEED(l.type != AGPT_LIGHT_INFINITE_AREA || c->envW > 0, AGPT_ERR_STATE, "InfiniteAreaLight without an environment map (agpt_upload_envmap)");
 	for (auto& l : c->hostLights)
@@ -261,18 +266,26 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
 // ---- launch helpers: template flags from run-time flags --------------------------------------
-static void LaunchClosest(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
-	if (count) { if (strictBoxes) k_trace_closest<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_closest<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
-	else { if (strictBoxes) k_trace_closest<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_closest<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
+// (COUNT, FAST = !strictBoxes, INST = the scene has instances) -> one of eight instantiations
+#define AGPT_DISPATCH3(count, fast, inst, CALL) do { \
+	if (count) { if (fast) { if (inst) { CALL(true, true, true); } else { CALL(true, true, false); } } else { if (inst) { CALL(true, false, true); } else { CALL(true, false, false); } } } \
+	else { if (fast) { if (inst) { CALL(false, true, true); } else { CALL(false, true, false); } } else { if (inst) { CALL(false, false, true); } else { CALL(false, false, false); } } } } while (0)
+
+static void LaunchClosest(bool count, bool strictBoxes, bool inst, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
+#define CALL(C, F, I) k_trace_closest<C, F, I><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row)
+	AGPT_DISPATCH3(count, !strictBoxes, inst, CALL);
+#undef CALL
 }
-static void LaunchAny(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
-	if (count) { if (strictBoxes) k_trace_any<true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_any<true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
-	else { if (strictBoxes) k_trace_any<false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); else k_trace_any<false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row); }
+static void LaunchAny(bool count, bool strictBoxes, bool inst, int blocks, cudaStream_t st, const DScene& sc, const PathState& ps, const int* queue, const int* n, unsigned long long* cnt, unsigned long long* row) {
+#define CALL(C, F, I) k_trace_any<C, F, I><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, ps, queue, n, cnt, row)
+	AGPT_DISPATCH3(count, !strictBoxes, inst, CALL);
+#undef CALL
 }
 template <bool ANY>
-static void LaunchTable(bool count, bool strictBoxes, int blocks, cudaStream_t st, const DScene& sc, const float4* o, const float4* d, int n, agpt_hit* out, unsigned long long* cnt) {
-	if (count) { if (strictBoxes) k_trace_table<ANY, true, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); else k_trace_table<ANY, true, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); }
-	else { if (strictBoxes) k_trace_table<ANY, false, false><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); else k_trace_table<ANY, false, true><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt); }
+static void LaunchTable(bool count, bool strictBoxes, bool inst, int blocks, cudaStream_t st, const DScene& sc, const float4* o, const float4* d, int n, agpt_hit* out, unsigned long long* cnt) {
+#define CALL(C, F, I) k_trace_table<ANY, C, F, I><<<blocks, AGPT_TRACE_THREADS, 0, st>>>(sc, o, d, n, out, cnt)
+	AGPT_DISPATCH3(count, !strictBoxes, inst, CALL);
+#undef CALL
 }
 
 
@@ -336,7 +349,7 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	for (int r = 0; r < c->peerWorld; r++) if (r != c->peerRank && c->peerAccum[r]) cudaIpcCloseMemHandle(c->peerAccum[r]);
 	for (auto& m : c->meshStore) m.Free();
-	c->meshes.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
+	c->meshes.Free(); c->instances.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free(); c->resolved.Free();
 	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
@@ -488,6 +501,8 @@ int agpt_upload_primitives(agpt_ctx* c, const agpt_prim* rows, int n) {
 	return AGPT_OK;
 }
 
+SIMPLE_UPLOAD(agpt_upload_instances, agpt_instance, instances, c->nInstances = n; c->hostInstances.assign(rows, rows + n))
+
 int agpt_upload_envmap(agpt_ctx* c, const agpt_envmap* env) {
 	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
 	CU(cudaSetDevice(c->device));
@@ -530,7 +545,7 @@ int agpt_set_film(agpt_ctx* c, int width, int height) {
 
 int agpt_scene_bytes(agpt_ctx* c, uint64_t* out) {
 	NEED(c != nullptr && out != nullptr, AGPT_ERR_INVALID, "null argument");
-	uint64_t b = c->envRgb.Bytes() + c->envFunc.Bytes() + c->envCdf.Bytes() + c->meshes.Bytes() + c->spheres.Bytes() + c->planes.Bytes() + c->prims.Bytes() + c->mats.Bytes() + c->lights.Bytes();
+	uint64_t b = c->envRgb.Bytes() + c->envFunc.Bytes() + c->envCdf.Bytes() + c->meshes.Bytes() + c->spheres.Bytes() + c->planes.Bytes() + c->prims.Bytes() + c->instances.Bytes() + c->mats.Bytes() + c->lights.Bytes();
 	for (auto& m : c->meshStore) b += m.nodes.Bytes() + m.tris.Bytes() + m.normals.Bytes() + m.uvs.Bytes() + m.ids.Bytes();
 	*out = b;
 	return AGPT_OK;
@@ -691,7 +706,7 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		if (timing) CU(cudaEventRecord(c->evA, c->stream));
 		if (fork) CU(cudaEventRecord(c->evFork, c->stream));
 		if (ubClosest > 0) {
-			LaunchClosest(count, strictBoxes, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest,
+			LaunchClosest(count, strictBoxes, c->nInstances > 0, Blocks(ubClosest, AGPT_TRACE_THREADS), c->stream, sc, ps, closestQueue, q[cur].counts + 0, cntClosest,
 				waveRows + (size_t)AGPT_WAVE_COUNTERS * (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1));
 			c->stats.kernel_launches++; c->stats.launches_closest++;
 		}
@@ -704,20 +719,20 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		if (timing) CU(cudaEventRecord(c->evB, c->stream));
 		if (fork) {
 			CU(cudaStreamWaitEvent(c->sideStream, c->evFork, 0));
-			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->sideStream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
+			LaunchAny(count, strictBoxes, c->nInstances > 0, Blocks(ubShadow, AGPT_TRACE_THREADS), c->sideStream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
 				waveRows + (size_t)AGPT_WAVE_COUNTERS * (AGPT_MAX_WAVE_ROWS + (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1)));
 			c->stats.kernel_launches++; c->stats.launches_any++;
 			CU(cudaEventRecord(c->evJoin, c->sideStream));
 			CU(cudaStreamWaitEvent(c->stream, c->evJoin, 0));
 		} else if (ubShadow > 0) {
-			LaunchAny(count, strictBoxes, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
+			LaunchAny(count, strictBoxes, c->nInstances > 0, Blocks(ubShadow, AGPT_TRACE_THREADS), c->stream, sc, ps, shadowQueue, q[cur].counts + 1, cntAny,
 				waveRows + (size_t)AGPT_WAVE_COUNTERS * (AGPT_MAX_WAVE_ROWS + (wave < AGPT_MAX_WAVE_ROWS ? wave : AGPT_MAX_WAVE_ROWS - 1)));
 			c->stats.kernel_launches++; c->stats.launches_any++;
 		}
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
-		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg;
+		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg; sp.rr_by_bounce = (flags & AGPT_FLAG_RR_BY_BOUNCE) ? 1 : 0;
 		// shade: k_shade_a (per active entry: NEE fold, emission, termination -> survivor list),
 		// then k_shade_b (per survivor: the BSDF work), blocks striding over the list
 		CU(cudaMemsetAsync(c->survivorCount.p, 0, sizeof(int), c->stream));
@@ -830,8 +845,8 @@ static int TraceTable(agpt_ctx* c, const DScene& sc, const float4* rayO, const f
 	CU(out.Alloc(n));
 	const bool count = flags & AGPT_FLAG_COUNTERS, strictBoxes = flags & AGPT_FLAG_STRICT_BOXES;
 	int blocks = Blocks(n, AGPT_TRACE_THREADS);
-	if (any_hit) LaunchTable<true>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p + AGPT_WAVE_COUNTERS);
-	else LaunchTable<false>(count, strictBoxes, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p);
+	if (any_hit) LaunchTable<true>(count, strictBoxes, c->nInstances > 0, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p + AGPT_WAVE_COUNTERS);
+	else LaunchTable<false>(count, strictBoxes, c->nInstances > 0, blocks, c->stream, sc, rayO, rayD, n, out.p, c->traceCounters.p);
 	CU(cudaGetLastError());
 	c->stats.kernel_launches++;
 	CU(cudaMemcpyAsync(out_host, out.p, (size_t)n * sizeof(agpt_hit), cudaMemcpyDeviceToHost, c->stream));
@@ -890,7 +905,7 @@ int agpt_trace_rays(agpt_ctx* c, int64_t n, const float* rays7, int any_hit, uin
 	return rcode;
 }
 
-static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, float* out_rgb) {
+static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, uint32_t flags, float* out_rgb) {
 	int n = g.n;
 	int rcode = EnsureCapacity(c, (size_t)n);
 	if (rcode != AGPT_OK) return rcode;
@@ -903,7 +918,7 @@ static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, 
 	c->stats.kernel_launches++;
 	c->stats.paths += (uint64_t)n;
 	c->stats.rays_closest += (uint64_t)n;
-	rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, 0);
+	rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, flags & AGPT_FLAG_RR_BY_BOUNCE);
 	if (rcode != AGPT_OK) return rcode;
 	std::vector<float4> host(n);
 	CU(cudaMemcpyAsync(host.data(), ps.Lout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -912,7 +927,7 @@ static int LiGeneric(agpt_ctx* c, GenParams g, int max_depth, int rr_depth_arg, 
 	return AGPT_OK;
 }
 
-int agpt_li_pixels(agpt_ctx* c, int n, const int* xs, const int* ys, const int* ss, int max_depth, int rr_depth_arg, float* out_rgb) {
+int agpt_li_pixels(agpt_ctx* c, int n, const int* xs, const int* ys, const int* ss, int max_depth, int rr_depth_arg, uint32_t flags, float* out_rgb) {
 	int rcode = CheckReady(c, true);
 	if (rcode != AGPT_OK) return rcode;
 	NEED(n >= 0 && (n == 0 || (xs && ys && ss && out_rgb)), AGPT_ERR_INVALID, "bad pixel list");
@@ -923,7 +938,7 @@ int agpt_li_pixels(agpt_ctx* c, int n, const int* xs, const int* ys, const int* 
 	GenParams g;
 	memset(&g, 0, sizeof(g));
 	g.n = n; g.xs = dx.p; g.ys = dy.p; g.ss = ds.p;
-	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
+	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, flags, out_rgb);
 	dx.Free(); dy.Free(); ds.Free();
 	return rcode;
 }
@@ -941,7 +956,7 @@ int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_sta
 	GenParams g;
 	memset(&g, 0, sizeof(g));
 	g.n = n; g.rays7 = rays.p; g.seeds = seeds.p; g.raysFinal = (flags & AGPT_FLAG_RAYS_FINAL) ? 1 : 0;
-	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, out_rgb);
+	rcode = LiGeneric(c, g, max_depth, rr_depth_arg, flags, out_rgb);
 	rays.Free(); seeds.Free();
 	return rcode;
 }

@@ -214,9 +214,12 @@ __device__ __forceinline__ void PlaneSurface(float3 O, float3 D, float t, DSurfa
 	SurfaceInit(s, O + t * D, f3(0, 0, 1), f3(1, 0, 0));
 }
 // Triangle hit -> interaction + shading frame (trianglemesh.cpp:45-113, intersectable.h:80-89)
-__device__ __forceinline__ void TriangleSurface(const DMesh& mesh, int slot, float3 O, float3 D, float t, float b1, float b2, DSurface& s) {
+// `in` (extension, agpt.h agpt_instance): the mesh is a placed one -- vertices go to world space first, the shading
+// normal through transpose(W2O); nullptr for the reference's own meshes.
+__device__ __forceinline__ void TriangleSurface(const DMesh& mesh, int slot, float3 O, float3 D, float t, float b1, float b2, DSurface& s, const agpt_instance* in) {
 	float4 a = __ldg(mesh.tris + 3 * slot), b = __ldg(mesh.tris + 3 * slot + 1), c = __ldg(mesh.tris + 3 * slot + 2);
 	float3 v0 = f3(a.x, a.y, a.z), v1 = f3(b.x, b.y, b.z), v2 = f3(c.x, c.y, c.z);
+	if (in) { v0 = XformPoint(in->object_to_world, v0); v1 = XformPoint(in->object_to_world, v1); v2 = XformPoint(in->object_to_world, v2); }
 	float b0 = 1.f - b1 - b2;
 	float2 uv0 = make_float2(0, 0), uv1 = make_float2(1, 0), uv2 = make_float2(1, 1);
 	if (mesh.uvs) { uv0 = __ldg(mesh.uvs + 3 * slot); uv1 = __ldg(mesh.uvs + 3 * slot + 1); uv2 = __ldg(mesh.uvs + 3 * slot + 2); }
@@ -226,6 +229,7 @@ __device__ __forceinline__ void TriangleSurface(const DMesh& mesh, int slot, flo
 	if (mesh.normals) {
 		float4 na = __ldg(mesh.normals + 3 * slot), nb = __ldg(mesh.normals + 3 * slot + 1), nc = __ldg(mesh.normals + 3 * slot + 2);
 		float3 ns = f3(na.x, na.y, na.z) * b0 + f3(nb.x, nb.y, nb.z) * b1 + f3(nc.x, nc.y, nc.z) * b2;
+		if (in) ns = XformNormal(in->world_to_object, ns);
 		if (sqrLength(ns) > 0.f) ns = normalize(ns);
 		else ns = s.n;
 		float3 ss = normalize(dpdu);

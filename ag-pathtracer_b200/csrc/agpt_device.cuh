@@ -50,6 +50,7 @@ struct DScene {
 	const agpt_sphere* spheres;
 	const agpt_plane* planes;
 	const DMesh* meshes;
+	const agpt_instance* instances;  // extension: placed meshes (rows of AGPT_PRIM_INSTANCE)
 	const agpt_material* mats;
 	const agpt_light* lights;
 	int n_prims, n_lights;
@@ -94,6 +95,17 @@ __device__ __forceinline__ bool IsBlack(float3 v) { return v.x == 0 && v.y == 0 
 __device__ __forceinline__ float3 Faceforward(float3 v, float3 v2) { return (dot(v, v2) < 0.f) ? -v : v; }   // precomp.h:712
 __device__ __forceinline__ float3 Lerp(float t, float3 a, float3 b) { return (1 - t) * a + t * b; }          // precomp.h:676
 __device__ __forceinline__ float3 Reflect(float3 wo, float3 n) { return -wo + 2.0f * dot(wo, n) * n; }        // precomp.h:762
+
+// EXTENSION: instances (agpt.h agpt_instance; CPU statement: oracle/agpt_oracle.cpp XformPoint / XformVector).
+__device__ __forceinline__ float3 XformPoint(const float* m, float3 p) {
+	return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+__device__ __forceinline__ float3 XformVector(const float* m, float3 v) {
+	return f3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z);
+}
+__device__ __forceinline__ float3 XformNormal(const float* w2o, float3 n) {        // transpose(W2O)
+	return f3(w2o[0] * n.x + w2o[4] * n.y + w2o[8] * n.z, w2o[1] * n.x + w2o[5] * n.y + w2o[9] * n.z, w2o[2] * n.x + w2o[6] * n.y + w2o[10] * n.z);
+}
 
 // template fminf/fmaxf (precomp.h:364-365) and clamp (precomp.h:678)
 __device__ __forceinline__ float rmin(float a, float b) { return a < b ? a : b; }

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_generate(DScene sc, PathState ps, WaveQ
 }
 
 // ---- trace kernels ---------------------------------------------------------------------
-template <bool COUNT, bool FAST>
+template <bool COUNT, bool FAST, bool INST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_closest(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
 		unsigned long long* counters, unsigned long long* waveRow) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 		d = kind ? ps.misD[path] : ps.rayD[path];
 	}
 	HitRecord hit;
-	TraceScene<false, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	TraceScene<false, COUNT, FAST, INST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) {
 		if (kind == 0) {
 			ps.hitA[path] = make_float4(hit.t, hit.b1, hit.b2, __int_as_float(hit.prim));
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 	if (COUNT) FlushCounters(cnt, lane, counters, waveRow);
 }
 
-template <bool COUNT, bool FAST>
+template <bool COUNT, bool FAST, bool INST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_trace_any(DScene sc, PathState ps, const int* __restrict__ queue, const int* __restrict__ countPtr,
 		unsigned long long* counters, unsigned long long* waveRow) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -316,13 +316,13 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS, AGPT_TRACE_MIN_BLOCKS) k_t
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = ps.shO[path]; d = ps.shD[path]; }
 	HitRecord hit;
-	bool occluded = TraceScene<true, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	bool occluded = TraceScene<true, COUNT, FAST, INST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) ps.shadowOccluded[path] = occluded ? 1 : 0;
 	if (COUNT) FlushCounters(cnt, lane, counters, waveRow);
 }
 
 // Standalone rays (agpt_trace_rays / agpt_trace_primary): hit table out.
-template <bool ANY, bool COUNT, bool FAST>
+template <bool ANY, bool COUNT, bool FAST, bool INST>
 __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, const float4* __restrict__ rayO, const float4* __restrict__ rayD,
 		int count, agpt_hit* out, unsigned long long* counters) {
 	__shared__ unsigned stackMem[AGPT_STACK_SMEM * AGPT_TRACE_THREADS];
@@ -332,13 +332,13 @@ __global__ void __launch_bounds__(AGPT_TRACE_THREADS) k_trace_table(DScene sc, c
 	float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 0.f, 0.f, 0.f);
 	if (lane) { o = rayO[i]; d = rayD[i]; }
 	HitRecord hit;
-	bool found = TraceScene<ANY, COUNT, FAST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
+	bool found = TraceScene<ANY, COUNT, FAST, INST>(sc, f3(o.x, o.y, o.z), f3(d.x, d.y, d.z), o.w, hit, stackMem + threadIdx.x, AGPT_TRACE_THREADS, cnt, lane);
 	if (lane) {
 		agpt_hit h;
 		h.found = found ? 1u : 0u;
 		h.prim = (found && !ANY) ? hit.prim : -1;
 		h.tri = -1;
-		if (found && !ANY && hit.slot >= 0) h.tri = sc.meshes[sc.prims[hit.prim].payload].ids[hit.slot];
+		if (found && !ANY && hit.slot >= 0) h.tri = MeshOfPrim<INST>(sc, sc.prims[hit.prim]).ids[hit.slot];
 		h.t = (found && !ANY) ? hit.t : 0.f;
 		out[i] = h;
 	}
@@ -350,6 +350,7 @@ struct ShadeParams {
 	const int* count;     // entries in the survivor list (this wave), on the device
 	int max_depth;
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
+	int rr_by_bounce;     // AGPT_FLAG_RR_BY_BOUNCE: roulette keyed on the bounce index instead (extension)
 };
 
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
@@ -507,7 +508,11 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			// SurfaceInteraction of the closest hit
 			if (prim.type == AGPT_PRIM_SPHERE) SphereSurface(sc.spheres[prim.payload], O, D, h.x, si);
 			else if (prim.type == AGPT_PRIM_PLANE) PlaneSurface(O, D, h.x, si);
-			else TriangleSurface(sc.meshes[prim.payload], hitSlot, O, D, h.x, h.y, h.z, si);
+			else if (prim.type == AGPT_PRIM_INSTANCE) {          // extension: a placed mesh
+				const agpt_instance& in = sc.instances[prim.payload];
+				TriangleSurface(sc.meshes[in.mesh], hitSlot, O, D, h.x, h.y, h.z, si, &in);
+			}
+			else TriangleSurface(sc.meshes[prim.payload], hitSlot, O, D, h.x, h.y, h.z, si, nullptr);
 
 			if (prim.material < 0) {
 				// null material: pass straight through, bounce count unchanged (integrator.h:152-161)
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 				specularBounce = sampledSpecular;
 				// Russian roulette (integrator.h:179-185): live only if the caller passed depth > 3
 				float maxComponent = smax(beta.x, smax(beta.y, beta.z));
-				if (maxComponent < 1 && sp.rr_depth_arg > 3) {
+				if (maxComponent < 1 && (sp.rr_by_bounce ? bounces : sp.rr_depth_arg) > 3) {
 					float q = smax(.05f, 1 - maxComponent);
 					if (RandomFloat(rng) < q) alive = false;
 					else beta /= 1 - q;

@@ -83,6 +83,26 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 	return BoundsIntersect(bmin, bmax, O, D, rayT, dist);
 }
 
+// exact-filtered slab test (agpt_device.cuh): valid only for sane direction and origin components
+template <bool FAST>
+__device__ __forceinline__ bool FilterOk(float3 O, float3 D) {
+	return FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
+		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
+}
+
+// EXTENSION: instances (agpt.h agpt_instance); the transforms themselves are in agpt_device.cuh.
+template <bool FAST>
+__device__ __forceinline__ void ObjectSpaceRay(const agpt_instance& in, float3 O, float3 D, float3& o, float3& d, float3& rd, bool& filterOk) {
+	o = XformPoint(in.world_to_object, O);
+	d = XformVector(in.world_to_object, D);        // not re-normalised: t means the same in both spaces
+	rd = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	filterOk = FilterOk<FAST>(o, d);
+}
+template <bool INST>
+__device__ __forceinline__ const DMesh& MeshOfPrim(const DScene& sc, const agpt_prim& pr) {
+	return sc.meshes[(INST && pr.type == AGPT_PRIM_INSTANCE) ? sc.instances[pr.payload].mesh : pr.payload];
+}
+
 #ifndef AGPT_ANY_NEAR_FIRST
 #define AGPT_ANY_NEAR_FIRST 1
 #endif
@@ -109,7 +129,7 @@ __device__ __forceinline__ bool ExactBoxHit(float3 bmin, float3 bmax, float3 O, 
 // tests is the reference's; the root tests just happen in lockstep instead of one loop step
 // each (a typical ray hits 1-2 of 5 roots).
 // `lane` is false for threads without a ray; they must still call (full-mask votes).
-template <bool ANY, bool COUNT, bool FAST>
+template <bool ANY, bool COUNT, bool FAST, bool INST>
 __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, float3 O, float3 D, float3 rD, bool filterOk, float& rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	bool found = false;
@@ -117,13 +137,24 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 	unsigned cand = 0;               // meshes of the run this lane still has to enter (bit m - p0)
 	unsigned bvhMask = 0;            // meshes of the run that have a root box
 	const float rayT0 = rayT;
+	// INST (the scene has instances, agpt.h agpt_instance): a mesh of the run may be a placed one; its boxes and
+	// triangles are then tested against the object-space ray (cO, cD), which shares the parameter t with the world ray.
+	float3 cO = O, cD = D, crD = rD;
+	bool cFilt = filterOk;
 	for (int m = p0; m < p1; m++) {
-		const DMesh& mesh = sc.meshes[sc.prims[m].payload];
+		const agpt_prim pr = sc.prims[m];
+		const DMesh& mesh = MeshOfPrim<INST>(sc, pr);
 		bool c = lane;
 		if (COUNT && mesh.nodes != nullptr) bvhMask |= 1u << (m - p0);
 		if (c && mesh.nodes != nullptr) {
 			NodeBox root = LoadNode(mesh.nodes, 0);
-			c = ExactBoxHit<FAST>(root.bmin, root.bmax, O, D, rD, filterOk, rayT0);
+			if (INST && pr.type == AGPT_PRIM_INSTANCE) {
+				float3 o, d, rd;
+				bool f;
+				ObjectSpaceRay<FAST>(sc.instances[pr.payload], O, D, o, d, rd, f);
+				c = ExactBoxHit<FAST>(root.bmin, root.bmax, o, d, rd, f, rayT0);
+			}
+			else c = ExactBoxHit<FAST>(root.bmin, root.bmax, O, D, rD, filterOk, rayT0);
 		}
 		if (c) cand |= 1u << (m - p0);
 	}
@@ -142,15 +173,20 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 				int bit = __ffs((int)cand) - 1;
 				cand &= cand - 1u;
 				mp = p0 + bit;
-				const DMesh& mesh = sc.meshes[sc.prims[mp].payload];
+				const agpt_prim pr = sc.prims[mp];
+				const DMesh& mesh = MeshOfPrim<INST>(sc, pr);
 				nodes = mesh.nodes; tris = mesh.tris;
+				if (INST) {
+					if (pr.type == AGPT_PRIM_INSTANCE) ObjectSpaceRay<FAST>(sc.instances[pr.payload], O, D, cO, cD, crD, cFilt);
+					else { cO = O; cD = D; crD = rD; cFilt = filterOk; }
+				}
 				if (nodes == nullptr) {
 					// plain TriangleMesh: every triangle in order, no bounds test (trianglemesh.h:25-41)
 					for (int j = 0; j < mesh.n_tris; j++) {
 						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
-						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), cO, cD, rayT, t, b1, b2)) {
 							found = true;
 							if (ANY) break;
 							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
@@ -160,7 +196,7 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 				else {
 					NodeBox root = LoadNode(nodes, 0);
 					// ray.t unchanged since the prepass: same decision; else redo it with the shrunken extent
-					if (rayT == rayT0 || ExactBoxHit<FAST>(root.bmin, root.bmax, O, D, rD, filterOk, rayT)) {
+					if (rayT == rayT0 || ExactBoxHit<FAST>(root.bmin, root.bmax, cO, cD, crD, cFilt, rayT)) {
 						cur = EncodeNode(0, root.first, root.count); sp = 0; inside = true;
 					}
 				}
@@ -169,15 +205,16 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 				bool pop = true;
 				if (!(cur & (AGPT_ENT_LEAF1 | AGPT_ENT_LEAFN))) {
 					// interior: fetch the sibling pair (64 B), test both boxes
+					AGPT_CHECK((int)cur >= 2 && (int)cur + 1 < MeshOfPrim<INST>(sc, sc.prims[mp]).n_nodes, AGPT_DBG_NODE, cur);
 					NodeBox l = LoadNode(nodes, (int)cur), r = LoadNode(nodes, (int)cur + 1);
 					if (COUNT) { cnt.node_visits++; cnt.box_tests += 2; }
 					float dl, dr;
 					bool hl, hr, swapKids;
-					bool strict = !filterOk;
+					bool strict = !cFilt;
 					if (!strict) {
 						float xl, xr;
-						SlabApprox(l.bmin, l.bmax, O, rD, rayT, dl, xl);
-						SlabApprox(r.bmin, r.bmax, O, rD, rayT, dr, xr);
+						SlabApprox(l.bmin, l.bmax, cO, crD, rayT, dl, xl);
+						SlabApprox(r.bmin, r.bmax, cO, crD, rayT, dr, xr);
 						int cl = SlabDecision(dl, xl), cr = SlabDecision(dr, xr);
 						if (ANY && !COUNT && AGPT_ANY_NEAR_FIRST) {
 							// Occlusion does not depend on the order of the walk (upstream: left first,
@@ -194,8 +231,8 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						}
 					}
 					if (strict) {
-						hl = BoundsIntersect(l.bmin, l.bmax, O, D, rayT, dl);
-						hr = BoundsIntersect(r.bmin, r.bmax, O, D, rayT, dr);
+						hl = BoundsIntersect(l.bmin, l.bmax, cO, cD, rayT, dl);
+						hr = BoundsIntersect(r.bmin, r.bmax, cO, cD, rayT, dr);
 						// closest-hit: near first, far pushed iff both hit (swap iff rightDist < leftDist,
 						// bvhtrimesh.h:359-372); any-hit: left first (:400-411)
 						swapKids = ANY ? false : (dr < dl);
@@ -218,11 +255,12 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 						NodeBox n = LoadNode(nodes, (int)(cur & 0x3fffffffu));
 						first = n.first; count = n.count;
 					}
+					AGPT_CHECK(first >= 0 && first + count <= MeshOfPrim<INST>(sc, sc.prims[mp]).n_tris, AGPT_DBG_TRI, first);
 					for (int j = first; j < first + count; j++) {
 						float4 a = LoadTable(tris + 3 * j), b = LoadTable(tris + 3 * j + 1), c = LoadTable(tris + 3 * j + 2);
 						if (COUNT) cnt.tri_tests++;
 						float t, b1, b2;
-						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), O, D, rayT, t, b1, b2)) {
+						if ((ANY || a.w == 0.f) && TriangleTest(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), cO, cD, rayT, t, b1, b2)) {
 							found = true;
 							if (ANY) break;
 							rayT = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = mp; hit.slot = j;
@@ -253,15 +291,14 @@ __device__ __forceinline__ bool TraceMeshRun(const DScene& sc, int p0, int p1, f
 // (Testing the spheres and planes first and the meshes afterwards, with an exact tie-aware merge,
 // was measured: closest-hit +13 % on cfg 3, +10 % in the closed room -- a second pass over the
 // primitive list for little extra pruning.  Not kept; numbers in DESIGN.md.)
-template <bool ANY, bool COUNT, bool FAST>
+template <bool ANY, bool COUNT, bool FAST, bool INST>
 __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D, float rayT, HitRecord& hit,
 		unsigned* stack, int stackStride, TraceCounters& cnt, bool lane) {
 	hit.prim = -1; hit.slot = -1; hit.t = 0.f; hit.b1 = 0.f; hit.b2 = 0.f;
 	bool found = false;
 	// exact-filtered slab test (agpt_device.cuh): reciprocal direction, valid only for sane components
 	const float3 rD = f3(1.0f / D.x, 1.0f / D.y, 1.0f / D.z);
-	const bool filterOk = FAST && fabsf(D.x) >= 1e-18f && fabsf(D.y) >= 1e-18f && fabsf(D.z) >= 1e-18f &&
-		fabsf(D.x) <= 2.0f && fabsf(D.y) <= 2.0f && fabsf(D.z) <= 2.0f && fabsf(O.x) < 1e15f && fabsf(O.y) < 1e15f && fabsf(O.z) < 1e15f;
+	const bool filterOk = FilterOk<FAST>(O, D);
 	int p = 0;
 	while (p < sc.n_prims) {
 		agpt_prim prim = sc.prims[p];
@@ -314,7 +351,7 @@ __device__ __forceinline__ bool TraceScene(const DScene& sc, float3 O, float3 D,
 		else {
 			int q = p + 1;                                     // run of consecutive mesh primitives (<= 32 per call)
 			while (q < sc.n_prims && q < p + 32 && sc.prims[q].type >= AGPT_PRIM_BVH_MESH) q++;
-			if (TraceMeshRun<ANY, COUNT, FAST>(sc, p, q, O, D, rD, filterOk, rayT, hit, stack, stackStride, cnt, test)) found = true;
+			if (TraceMeshRun<ANY, COUNT, FAST, INST>(sc, p, q, O, D, rD, filterOk, rayT, hit, stack, stackStride, cnt, test)) found = true;
 			p = q;
 		}
 	}

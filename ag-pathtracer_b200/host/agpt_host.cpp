@@ -27,6 +27,7 @@ static int UploadFlat(const FlatScene& flat, const Camera& camera, agpt_ctx* ctx
 	if ((rc = agpt_upload_materials(ctx, flat.materials.data(), (int)flat.materials.size()))) return rc;
 	if ((rc = agpt_upload_lights(ctx, flat.lights.data(), (int)flat.lights.size()))) return rc;
 	if ((rc = agpt_upload_envmap(ctx, flat.envmap.width > 0 ? &flat.envmap : nullptr))) return rc;
+	if ((rc = agpt_upload_instances(ctx, flat.instances.data(), (int)flat.instances.size()))) return rc;
 	if ((rc = agpt_upload_primitives(ctx, flat.prims.data(), (int)flat.prims.size()))) return rc;
 	agpt_camera cam = camera.Export();
 	return agpt_set_camera(ctx, &cam);
@@ -94,6 +95,7 @@ int agpt_host_scene_tables(agpt_host_scene* s, agpt_scene_tables* out) {
 		out->lights = f.lights.data(); out->n_lights = (int)f.lights.size();
 		out->camera = s->camera->Export();
 		out->envmap = f.envmap;
+		out->instances = f.instances.data(); out->n_instances = (int)f.instances.size();
 	)
 	return AGPT_OK;
 }
@@ -112,7 +114,8 @@ int agpt_host_prim_info(agpt_host_scene* s, int prim, int* kind, int* counts5, i
 	*is_light = shape->GetAreaLight() != nullptr;
 	for (int i = 0; i < 5; i++) counts5[i] = 0;
 	if (*kind >= AGPT_PRIM_BVH_MESH) {
-		const agpt_mesh_desc& m = Flat(s).meshes[Flat(s).prims[prim].payload];
+		const int payload = Flat(s).prims[prim].payload;
+		const agpt_mesh_desc& m = Flat(s).meshes[*kind == AGPT_PRIM_INSTANCE ? Flat(s).instances[payload].mesh : payload];
 		counts5[0] = m.n_nodes; counts5[1] = m.n_tris;
 		counts5[3] = m.tri_normals ? 1 : 0; counts5[4] = m.tri_uvs ? 1 : 0;
 	}

@@ -53,6 +53,7 @@ public:
 			Check(agpt_upload_materials(ctx, flat->materials.data(), (int)flat->materials.size()));
 			Check(agpt_upload_lights(ctx, flat->lights.data(), (int)flat->lights.size()));
 			Check(agpt_upload_envmap(ctx, flat->envmap.width > 0 ? &flat->envmap : nullptr));
+			Check(agpt_upload_instances(ctx, flat->instances.data(), (int)flat->instances.size()));
 			Check(agpt_upload_primitives(ctx, flat->prims.data(), (int)flat->prims.size()));
 		}
 		uploaded = scene.Fingerprint();

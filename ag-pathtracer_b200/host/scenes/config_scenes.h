@@ -41,6 +41,7 @@ inline ConfigDefaults Defaults(int config) {
 	case 6: return { 320, 180, 16, 5, 0, "cfg6_test_thin_lens_plain_mesh_multi_tri_leaves" };
 	case 7: return { 400, 400, 64, 5, 0, "cfg7_reference_default_scene_envmap_400x400" };
 	case 8: return { 640, 360, 16, 6, 4, "cfg8_test_degenerate_triangles_deep_tree_overflowing_light" };
+	case 9: return { 3840, 2160, 1024, 8, 0, "cfg9_ext_cfg4_with_true_instances_one_mesh_8_placements" };
 	default: return { 0, 0, 0, 0, 0, "unknown" };
 	}
 }
@@ -468,6 +469,35 @@ inline void BuildConfig8(Scene* scene, int level) {
 	scene->camera.aperture = 0;
 }
 
+#ifdef AGPT_HAS_INSTANCES
+// cfg 9 (EXTENSION, host mirror only -- the reference has no Instance class): BASELINE config 4 as its wording has it,
+// "10M-triangle INSTANCED scene": ONE unit icosphere mesh (level 8 = 1,310,720 triangles, one BVH) placed eight times
+// on the 2x2x2 lattice of cfg 4 through per-instance transforms, one of them scaled and rotated, each placement with
+// its own material.  The scene holds 1/8 of cfg 4's geometry (215 MB instead of 1.7 GB).
+inline void BuildConfig9(Scene* scene, int level) {
+	auto grey = DisneyMaterial::Make(float3(.5f, .5f, .5f), 1.f, 0.f);
+	scene->primitives.push_back(std::make_shared<Plane>(float3(0, -2.5f, 0), float2(60, 60), grey));
+	const int palette[8] = { 0xf19a91, 0x9ed5d8, 0xeecf74, 0x87abc5, 0xc4ac64, 0x69bab3, 0xe57a82, 0xf7f7f7 };
+	auto unit = MakeIcosphere(level, float3(0, 0, 0), 1.f, grey);
+	auto shared = std::make_shared<BVHTriMesh>(unit, grey, 1);
+	for (int i = 0; i < 8; i++) {
+		auto m = DisneyMaterial::Make(hex2lin(palette[i]), .2f + .1f * i, (i % 3 == 2) ? 1.f : 0.f);
+		mat4 xf = mat4::Translate((i & 1) ? 1.25f : -1.25f, (i & 2) ? 1.25f : -1.25f, (i & 4) ? 1.25f : -1.25f);
+		if (i == 5) xf = xf * mat4::RotateY(.6f) * mat4::Scale(.8f);          // a placement that is not a pure translation
+		scene->primitives.push_back(std::make_shared<Instance>(shared, xf, m));
+	}
+	scene->addAreaLight(std::make_shared<Sphere>(float3(0, 25, -20), 1.f, nullptr), WarmWhite(200));
+	scene->addAreaLight(std::make_shared<Sphere>(float3(-12, 10, -6), 1.f, nullptr), WarmWhite(60));
+	scene->lights.push_back(std::make_shared<UniformInfiniteLight>(float3(.2f, .22f, .25f)));
+	scene->camera.lookfrom = float3(4.5f, 3.5f, -9.f);
+	scene->camera.lookat = float3(0, 0, 0);
+	scene->camera.vup = float3(0, 1, 0);
+	scene->camera.aspect_ratio = 16.f / 9.f;
+	scene->camera.vfov = 35;
+	scene->camera.aperture = 0;
+}
+#endif
+
 // level <= 0 selects the BASELINE.json size of each configuration.
 inline bool BuildConfig(Scene* scene, int config, int level) {
 	switch (config) {
@@ -479,6 +509,9 @@ inline bool BuildConfig(Scene* scene, int config, int level) {
 	case 6: BuildConfig6(scene, level > 0 ? level : 2); return true;
 	case 7: BuildConfig7(scene); return true;
 	case 8: BuildConfig8(scene, level > 0 ? level : 3); return true;
+#ifdef AGPT_HAS_INSTANCES
+	case 9: BuildConfig9(scene, level > 0 ? level : 8); return true;
+#endif
 	default: return false;
 	}
 }

@@ -78,7 +78,24 @@ typedef struct agpt_plane {      /* intersectable.h:119-121,154-156: XZ plane th
 	float pad[3];
 } agpt_plane;
 
-enum { AGPT_PRIM_SPHERE = 0, AGPT_PRIM_PLANE = 1, AGPT_PRIM_BVH_MESH = 2, AGPT_PRIM_MESH = 3 };
+enum { AGPT_PRIM_SPHERE = 0, AGPT_PRIM_PLANE = 1, AGPT_PRIM_BVH_MESH = 2, AGPT_PRIM_MESH = 3,
+       AGPT_PRIM_INSTANCE = 4 /* EXTENSION: a placed mesh, payload = index into the instance table */ };
+
+/* EXTENSION (BASELINE config 4 says "instanced"): one placement of a mesh.  The reference has no
+ * transforms at trace time (scene.h:5-28: a flat list, geometry baked); what an instance means is therefore
+ * defined here and stated on the CPU in oracle/agpt_oracle.cpp (parity is against that, not against the reference):
+ *   - the ray is taken to object space, O' = W2O * (O,1), D' = W2O * (D,0), D' NOT re-normalised, so the ray
+ *     parameter t is the same in both spaces and ray.t is shared with the rest of the scene;
+ *   - BVHTriMesh::Intersect / IntersectP run unchanged on (O', D', t) over the shared mesh;
+ *   - the hit point is O + t*D (world ray); the triangle's vertices go to world space through O2W before the
+ *     partial derivatives are formed, the interpolated shading normal goes through transpose(W2O).
+ * Matrices are 3x4 row-major affine, rows of [R | t]; products are summed left to right ((m0*x + m1*y) + m2*z) + m3. */
+typedef struct agpt_instance {
+	int32_t mesh;                  /* index into the mesh table (shared by any number of instances) */
+	int32_t pad[3];
+	float object_to_world[12];
+	float world_to_object[12];
+} agpt_instance;
 
 /* Scene::primitives in list order (scene.h:5-13,27): order decides exact-t ties. */
 typedef struct agpt_prim {
@@ -182,8 +199,12 @@ enum {
 	AGPT_FLAG_TIMING = 2u,        /* bracket every kernel class with CUDA events (serialises) */
 	AGPT_FLAG_STRICT_BOXES = 4u,  /* every slab test with the reference's six IEEE divisions; the default is the
 	                                 exact-filtered test (same decisions, divisions only inside a guard band) */
-	AGPT_FLAG_RAYS_FINAL = 8u     /* agpt_trace_rays / agpt_li_rays: directions are used as given -- the rays come from host
+	AGPT_FLAG_RAYS_FINAL = 8u,    /* agpt_trace_rays / agpt_li_rays: directions are used as given -- the rays come from host
 	                                 Ray objects, whose constructor has normalised them already (camera.h:7) */
+	AGPT_FLAG_RR_BY_BOUNCE = 16u  /* EXTENSION (not reference behaviour): Russian roulette keyed on the path's own
+	                                 bounce index -- live once bounces > 3, the rule BASELINE config 5 names ("16 bounces with Russian
+	                                 roulette") -- instead of on Li's constant depth argument (integrator.h:180, dead for depth = 0).
+	                                 rr_depth_arg is ignored.  Checked against oracle/agpt_oracle.cpp, the only statement of it. */
 };
 
 /* ---- lifecycle --------------------------------------------------------------------- */
@@ -201,6 +222,7 @@ int agpt_upload_meshes(agpt_ctx* ctx, const agpt_mesh_desc* meshes, int n);
 int agpt_upload_spheres(agpt_ctx* ctx, const agpt_sphere* spheres, int n);
 int agpt_upload_planes(agpt_ctx* ctx, const agpt_plane* planes, int n);
 int agpt_upload_primitives(agpt_ctx* ctx, const agpt_prim* prims, int n);
+int agpt_upload_instances(agpt_ctx* ctx, const agpt_instance* instances, int n);  /* EXTENSION; rows of AGPT_PRIM_INSTANCE point here */
 int agpt_upload_materials(agpt_ctx* ctx, const agpt_material* materials, int n);
 int agpt_upload_lights(agpt_ctx* ctx, const agpt_light* lights, int n);
 int agpt_upload_envmap(agpt_ctx* ctx, const agpt_envmap* env);          /* NULL clears it */
@@ -227,7 +249,7 @@ int agpt_trace_rays(agpt_ctx* ctx, int64_t n, const float* rays7, int any_hit, u
 /* Radiance of single camera paths without accumulation (Integrator::Li for the debug
  * click, myapp.cpp:196-198): pixel (xs[i], ys[i]), sample ss[i] -> out_rgb[3*i..]. */
 int agpt_li_pixels(agpt_ctx* ctx, int n, const int* xs, const int* ys, const int* ss,
-		int max_depth, int rr_depth_arg, float* out_rgb);
+		int max_depth, int rr_depth_arg, uint32_t flags, float* out_rgb);
 
 /* Integrator::Li(ray, scene, depth) for caller-supplied rays (integrator.h:28-31): rays7 as
  * in agpt_trace_rays, rng_states[i] = xorshift32 state the path starts from (the reference

@@ -46,6 +46,7 @@ typedef struct agpt_scene_tables {
 	const agpt_light* lights; int n_lights;
 	agpt_camera camera;
 	agpt_envmap envmap;      /* width == 0: none */
+	const agpt_instance* instances; int n_instances;      /* extension: placed meshes */
 } agpt_scene_tables;
 int agpt_host_scene_tables(agpt_host_scene* scene, agpt_scene_tables* out);
 

@@ -90,18 +90,28 @@ struct OScene {
 	std::vector<Mesh> meshes;
 	std::vector<agpt_material> mats;
 	std::vector<agpt_light> lights;
+	std::vector<agpt_instance> instances;    // extension: placed meshes (agpt.h)
 	agpt_camera cam;
 	// InfiniteAreaLight tables (lights.cpp:31-48, texture.h:41-57, sampling.h:22-35)
 	int envW = 0, envH = 0;
 	std::vector<float> envRgb, envFunc, envCdf;
 	float envFuncInt = 0;
+	bool rrByBounce = false;           // extension: Russian roulette keyed on the bounce index (see Li)
 };
 
 struct Ray {                       // camera.h:3-15
 	V3 O, D;
 	float t;
 	Ray(V3 o, V3 d, float tt = FLT_MAX) : O(o), D(normalize(d)), t(tt) {}
+	struct AsGiven {};             // object-space rays of instances keep their (unnormalised) direction: same t as in world space
+	Ray(AsGiven, V3 o, V3 d, float tt) : O(o), D(d), t(tt) {}
 };
+
+// ---- EXTENSION: instances (agpt.h agpt_instance).  Parity unpinned by the reference -- it has no transforms at trace
+// time; this is the statement the GPU path is checked against.  3x4 row-major affine, sums left to right.
+inline V3 XformPoint(const float* m, V3 p) { return v3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]); }
+inline V3 XformVector(const float* m, V3 v) { return v3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); }
+inline V3 XformNormal(const float* w2o, V3 n) { return v3(w2o[0] * n.x + w2o[4] * n.y + w2o[8] * n.z, w2o[1] * n.x + w2o[5] * n.y + w2o[9] * n.z, w2o[2] * n.x + w2o[6] * n.y + w2o[10] * n.z); }   // transpose(W2O)
 
 struct Counters {
 	uint64_t raysClosest = 0, raysAny = 0, interior = 0, boxes = 0, tris = 0, analytic = 0;
@@ -112,6 +122,8 @@ struct Hit {
 	int prim = -1, slot = -1;
 	float t = 0, b1 = 0, b2 = 0;
 };
+
+inline const Mesh& MeshOfPrim(const OScene& sc, const agpt_prim& pr) { return sc.meshes[pr.type == AGPT_PRIM_INSTANCE ? sc.instances[pr.payload].mesh : pr.payload]; }
 
 // Bounds::Intersect (bvhtrimesh.h:18-36), per-axis early out as written upstream
 bool BoundsIntersect(const agpt_bvh_node& n, const Ray& ray, float& t) {
@@ -273,6 +285,26 @@ bool SceneIntersect(const OScene& sc, Ray& ray, Hit& hit, Counters& c) {
 			c.analytic++;
 			if (PlaneTest(sc.planes[pr.payload], ray, t)) { ray.t = t; hit = Hit(); hit.t = t; hit.prim = (int)p; found = true; }
 		}
+		else if (pr.type == AGPT_PRIM_INSTANCE) {
+			// extension: the same two mesh entry points on the object-space ray; t is shared
+			const agpt_instance& in = sc.instances[pr.payload];
+			const Mesh& m = sc.meshes[in.mesh];
+			Ray local(Ray::AsGiven(), XformPoint(in.world_to_object, ray.O), XformVector(in.world_to_object, ray.D), ray.t);
+			bool any = false;
+			if (m.nodes.empty()) {
+				for (size_t j = 0; j < m.ids.size(); j++) {
+					c.tris++;
+					float b1, b2;
+					if (TriangleTest(m, (int)j, local, false, t, b1, b2)) { local.t = t; hit.t = t; hit.b1 = b1; hit.b2 = b2; hit.prim = (int)p; hit.slot = (int)j; any = true; }
+				}
+			}
+			else {
+				float dist;
+				c.boxes++;
+				if (BoundsIntersect(m.nodes[0], local, dist) && RecursiveHit(m, (int)p, m.nodes[0], local, hit, c)) any = true;
+			}
+			if (any) { ray.t = local.t; found = true; }
+		}
 		else {
 			const Mesh& m = sc.meshes[pr.payload];
 			if (m.nodes.empty()) {                                                        // TriangleMesh::Intersect (trianglemesh.h:25-35)
@@ -302,14 +334,16 @@ bool SceneIntersectP(const OScene& sc, const Ray& ray, Counters& c) {
 		if (pr.type == AGPT_PRIM_SPHERE) { c.analytic++; if (SphereTest(sc.spheres[pr.payload], ray, t)) return true; }
 		else if (pr.type == AGPT_PRIM_PLANE) { c.analytic++; if (PlaneTest(sc.planes[pr.payload], ray, t)) return true; }
 		else {
-			const Mesh& m = sc.meshes[pr.payload];
+			const bool inst = pr.type == AGPT_PRIM_INSTANCE;
+			const Mesh& m = sc.meshes[inst ? sc.instances[pr.payload].mesh : pr.payload];
+			const Ray local = inst ? Ray(Ray::AsGiven(), XformPoint(sc.instances[pr.payload].world_to_object, ray.O), XformVector(sc.instances[pr.payload].world_to_object, ray.D), ray.t) : ray;
 			if (m.nodes.empty()) {
-				for (size_t j = 0; j < m.ids.size(); j++) { c.tris++; float b1, b2; if (TriangleTest(m, (int)j, ray, true, t, b1, b2)) return true; }
+				for (size_t j = 0; j < m.ids.size(); j++) { c.tris++; float b1, b2; if (TriangleTest(m, (int)j, local, true, t, b1, b2)) return true; }
 			}
 			else {
 				float dist;
 				c.boxes++;
-				if (BoundsIntersect(m.nodes[0], ray, dist) && RecursiveHitP(m, m.nodes[0], ray, c)) return true;
+				if (BoundsIntersect(m.nodes[0], local, dist) && RecursiveHitP(m, m.nodes[0], local, c)) return true;
 			}
 		}
 	}
@@ -339,9 +373,11 @@ void BuildSurface(const OScene& sc, const Ray& ray, const Hit& h, Surface& s) {
 	}
 	else if (pr.type == AGPT_PRIM_PLANE) s.Init(ray.O + h.t * ray.D, v3(0, 0, 1), v3(1, 0, 0));   // :128-133
 	else {                                                                                // trianglemesh.cpp:45-113
-		const Mesh& m = sc.meshes[pr.payload];
+		const agpt_instance* in = pr.type == AGPT_PRIM_INSTANCE ? &sc.instances[pr.payload] : nullptr;
+		const Mesh& m = sc.meshes[in ? in->mesh : pr.payload];
 		const float* p = &m.verts[12 * (size_t)h.slot];
 		V3 v0 = v3(p), v1 = v3(p + 4), v2 = v3(p + 8);
+		if (in) { v0 = XformPoint(in->object_to_world, v0); v1 = XformPoint(in->object_to_world, v1); v2 = XformPoint(in->object_to_world, v2); }   // extension
 		float b0 = 1.f - h.b1 - h.b2;
 		float uv[6];
 		TriangleUVs(m, h.slot, uv);
@@ -351,6 +387,7 @@ void BuildSurface(const OScene& sc, const Ray& ray, const Hit& h, Surface& s) {
 		if (!m.normals.empty()) {
 			const float* q = &m.normals[12 * (size_t)h.slot];
 			V3 ns = v3(q) * b0 + v3(q + 4) * h.b1 + v3(q + 8) * h.b2;
+			if (in) ns = XformNormal(in->world_to_object, ns);                                // extension
 			if (sqrLength(ns) > 0.f) ns = normalize(ns);
 			else ns = s.n;
 			V3 ss = normalize(dpdu);
@@ -761,6 +798,8 @@ V3 EstimateDirect(const OScene& sc, const Surface& si, const Bsdf& bsdf, V3 wo, 
 }
 
 // PathTracer::Li (integrator.h:124-191)
+// sc.rrByBounce (EXTENSION, parity unpinned by the reference: it has no such rule): the roulette is keyed on the
+// path's bounce index -- `bounces > 3`, as PBRT states it -- instead of on the constant depth argument.
 V3 Li(const OScene& sc, Ray ray, int maxDepth, int depthArg, Rng& rng, Counters& c) {
 	V3 beta = v3(1.f), L = v3(0.f);
 	bool specularBounce = false;
@@ -807,7 +846,7 @@ V3 Li(const OScene& sc, Ray ray, int maxDepth, int depthArg, Rng& rng, Counters&
 		beta *= f * absdot(wi, si.sn) / pdf;
 		specularBounce = sampledSpecular;
 		float maxComponent = std::max(beta.x, std::max(beta.y, beta.z));
-		if (maxComponent < 1 && depthArg > 3) {                                           // :179-185
+		if (maxComponent < 1 && (sc.rrByBounce ? bounces : depthArg) > 3) {               // :179-185
 			float q = std::max(.05f, 1 - maxComponent);
 			if (rng.Float() < q) break;
 			beta /= 1 - q;
@@ -861,6 +900,7 @@ struct agpt_oracle_tables {            // what tests pass in: the flattened tabl
 	const agpt_light* lights; int n_lights;
 	agpt_camera camera;
 	agpt_envmap envmap;
+	const agpt_instance* instances; int n_instances;
 };
 
 void* agpt_oracle_scene_create(const agpt_oracle_tables* t) {
@@ -870,6 +910,7 @@ void* agpt_oracle_scene_create(const agpt_oracle_tables* t) {
 	s->planes.assign(t->planes, t->planes + t->n_planes);
 	s->mats.assign(t->materials, t->materials + t->n_materials);
 	s->lights.assign(t->lights, t->lights + t->n_lights);
+	if (t->n_instances > 0) s->instances.assign(t->instances, t->instances + t->n_instances);
 	s->cam = t->camera;
 	if (t->envmap.width > 0) {
 		size_t n = (size_t)t->envmap.width * t->envmap.height;
@@ -891,6 +932,7 @@ void* agpt_oracle_scene_create(const agpt_oracle_tables* t) {
 	return s;
 }
 void agpt_oracle_scene_destroy(void* h) { delete (OScene*)h; }
+void agpt_oracle_scene_set_rr_by_bounce(void* h, int on) { ((OScene*)h)->rrByBounce = on != 0; }
 
 // Same contract as agpt_ref_render (oracle/ref_harness.cpp).  counters_out (optional, 6):
 // closest rays, any-hit rays, interior visits, box tests, triangle tests, analytic tests.
@@ -940,7 +982,7 @@ long long agpt_oracle_primary_hits(void* h, int W, int H, int sample, int thread
 			agpt_hit& o = out[(size_t)y * W + x];
 			o.found = found ? 1u : 0u;
 			o.prim = found ? hit.prim : -1;
-			o.tri = (found && hit.slot >= 0) ? sc.meshes[sc.prims[hit.prim].payload].ids[hit.slot] : -1;
+			o.tri = (found && hit.slot >= 0) ? MeshOfPrim(sc, sc.prims[hit.prim]).ids[hit.slot] : -1;
 			o.t = found ? hit.t : 0.f;
 		}
 	});
@@ -963,7 +1005,7 @@ void agpt_oracle_trace_rays(void* h, long long n, const float* rays7, int any_hi
 		o.found = found ? 1u : 0u;
 		if (found) {
 			o.prim = hit.prim; o.t = hit.t;
-			o.tri = hit.slot >= 0 ? sc.meshes[sc.prims[hit.prim].payload].ids[hit.slot] : -1;
+			o.tri = hit.slot >= 0 ? MeshOfPrim(sc, sc.prims[hit.prim]).ids[hit.slot] : -1;
 		}
 	}
 	if (counters_out) { counters_out[0] = c.interior; counters_out[1] = c.boxes; counters_out[2] = c.tris; }

@@ -36,7 +36,7 @@ class _Tables(ctypes.Structure):       # agpt_oracle_tables (= agpt_scene_tables
     _fields_ = [("prims", c_void_p), ("n_prims", c_int), ("spheres", c_void_p), ("n_spheres", c_int), ("planes", c_void_p), ("n_planes", c_int),
                 ("meshes", c_void_p), ("n_meshes", c_int), ("materials", c_void_p), ("n_materials", c_int), ("lights", c_void_p), ("n_lights", c_int),
                 ("camera", c_float * 19), ("env_w", c_int), ("env_h", c_int), ("env_rgb", c_void_p), ("env_func", c_void_p), ("env_cdf", c_void_p),
-                ("env_func_int", c_float)]
+                ("env_func_int", c_float), ("instances", c_void_p), ("n_instances", c_int)]
 
 
 class PortScene:
@@ -48,7 +48,7 @@ class PortScene:
         self._h = c_void_p(lib().agpt_oracle_scene_create(host_scene.tables() if host_scene is not None else ctypes.byref(tables)))
 
     @classmethod
-    def from_tables(cls, prims, meshes=(), spheres=None, planes=None, materials=(), lights=None, camera=None):
+    def from_tables(cls, prims, meshes=(), spheres=None, planes=None, materials=(), lights=None, camera=None, instances=None):
         """prims / spheres / planes / lights: structured numpy arrays in the layouts of include/agpt.h;
         meshes: objects with .desc() -> agpt_mesh_desc (binding.RawMesh); materials: list of agpt_material."""
         t = _Tables()
@@ -57,6 +57,7 @@ class PortScene:
             setattr(t, name, arr.ctypes.data if arr is not None and len(arr) else None)
             setattr(t, count, 0 if arr is None else len(arr))
         put("prims", "n_prims", prims); put("spheres", "n_spheres", spheres); put("planes", "n_planes", planes); put("lights", "n_lights", lights)
+        put("instances", "n_instances", instances); keep.append(instances)
         if len(meshes):
             descs = (type(meshes[0].desc()) * len(meshes))(*[m.desc() for m in meshes])
             keep.append(descs)
@@ -68,6 +69,10 @@ class PortScene:
         if camera is not None:
             t.camera = (c_float * 19)(*[float(v) for v in camera])
         return cls(tables=t, keep=keep)
+
+    def set_rr_by_bounce(self, on=True):
+        """EXTENSION (not reference behaviour): Russian roulette keyed on the bounce index, bounces > 3."""
+        lib().agpt_oracle_scene_set_rr_by_bounce(self._h, c_int(1 if on else 0))
 
     def trace_rays(self, rays7, any_hit=False):
         rays7 = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
