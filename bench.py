@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--level", type=int, default=0, help="icosphere subdivision override (tests); 0 = the configuration's own")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
@@ -338,14 +338,23 @@ def main():
                     route = "peer-memory kernel over CUDA-IPC-mapped accumulators (rank-order sums)"
         return ctx, accum_t, route
 
+    _token = torch.zeros(1, device=dev) if world > 1 else None
+
+    def light_barrier(sync=True):
+        """One 4-byte NCCL all-reduce on the bench stream: kernels enqueued behind it start only after every rank has
+        reached it (dist.barrier() costs ~2 ms per call at N = 8 here; this costs a small-message all-reduce)."""
+        dist.all_reduce(_token)
+        if sync:
+            stream.synchronize()
+
     def exchange(ctx, accum_t, route):
         """Sum of all ranks' accumulators into every rank's (inside timed regions)."""
         if world == 1:
             return
         if route.startswith("peer"):
-            dist.barrier()                      # every rank has rendered
+            light_barrier(sync=False)           # every rank has rendered (agpt_render returns synchronised): the kernel below queues behind it
             ctx.allreduce_accum_peers()
-            dist.barrier()                      # every slice has landed everywhere
+            light_barrier()                     # every slice has landed everywhere
         else:
             dist.all_reduce(accum_t, op=dist.ReduceOp.SUM)
 
@@ -469,11 +478,11 @@ def main():
             ctx.write_accum(host_acc)                                   # every rank: its host film -> device
             pkg.multigpu.render_sharded(ctx, (1 + k) * spp_all, spp_all, depth, depth_arg, rank, world)
             if route.startswith("peer"):
-                dist.barrier()
+                light_barrier(sync=False)
                 if rank == 0:
                     rgb = ctx.reduce_resolve_peers((1 + k) * spp_all, keep_sum=True)      # fused sum + CopyToSurface -> host pixels
                     ctx.read_accum(host_acc)                            # the summed float film -> host
-                dist.barrier()
+                light_barrier()
             else:
                 dist.all_reduce(accum_t, op=dist.ReduceOp.SUM)
                 if rank == 0:
@@ -576,9 +585,9 @@ def main():
                 # sum of the accumulators (N > 1) + CopyToSurface, pixels on the root's host
                 if multi:
                     if oroute.startswith("peer"):
-                        dist.barrier()
+                        light_barrier(sync=False)
                         out = octx.reduce_resolve_peers(samples) if rank == 0 else None
-                        dist.barrier()
+                        light_barrier()
                         return out
                     dist.all_reduce(oacc, op=dist.ReduceOp.SUM)
                     return octx.resolve(samples) if rank == 0 else None
