@@ -24,6 +24,8 @@ FLAG_RR_BY_BOUNCE = 16
 
 MAT_DISNEY = 1
 MAT_MIRROR = 2
+MAT_GLASS = 3          # extension: rough dielectric (make_material: color = Kr = Kt, `metallic` slot = eta)
+LOBE_GLASS_REFLECT, LOBE_GLASS_TRANSMIT = 16, 32
 
 
 class AgptError(RuntimeError):

@@ -73,6 +73,7 @@ struct agpt_ctx {
 	DevBuf<agpt_instance> instances;     // extension: placed meshes
 	std::vector<agpt_instance> hostInstances;
 	int nInstances = 0;
+	bool hasGlass = false;        // some material is a rough dielectric (extension): shade runs the GLASS instantiation
 	DevBuf<int> sphereRun;
 	DevBuf<float4> sphereRunBox;
 	std::vector<agpt_sphere> hostSpheres;
@@ -488,7 +489,7 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	}
 SIMPLE_UPLOAD(agpt_upload_spheres, agpt_sphere, spheres, c->nSpheres = n; c->hostSpheres.assign(rows, rows + n); c->runsDirty = true)
 SIMPLE_UPLOAD(agpt_upload_planes, agpt_plane, planes, c->nPlanes = n)
-SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n)
+SIMPLE_UPLOAD(agpt_upload_materials, agpt_material, mats, c->nMats = n; c->hasGlass = false; for (int i = 0; i < n; i++) if (rows[i].lobes & (AGPT_LOBE_GLASS_REFLECT | AGPT_LOBE_GLASS_TRANSMIT)) c->hasGlass = true)
 SIMPLE_UPLOAD(agpt_upload_lights, agpt_light, lights, c->hostLights.assign(rows, rows + n))
 int agpt_upload_primitives(agpt_ctx* c, const agpt_prim* rows, int n) {
 	NEED(c != nullptr && n >= 0 && (n == 0 || rows != nullptr), AGPT_ERR_INVALID, "bad table");
@@ -738,14 +739,13 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		CU(cudaMemsetAsync(c->survivorCount.p, 0, sizeof(int), c->stream));
 		sp.count = c->survivorCount.p;
 		const int shadeBlocks = Blocks(ubActive, AGPT_SHADE_THREADS);      // upper bound: blocks past the survivor count return at once
-		if (c->envW > 0) {
-			k_shade_a<true><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
-			k_shade_b<true><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, c->survivors.p, q[cur ^ 1], sp, c->rayCounters.p);
-		}
-		else {
-			k_shade_a<false><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
-			k_shade_b<false><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, c->survivors.p, q[cur ^ 1], sp, c->rayCounters.p);
-		}
+		if (c->envW > 0) k_shade_a<true><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
+		else k_shade_a<false><<<Blocks(ubActive, 256), 256, 0, c->stream>>>(sc, ps, qin.active, q[cur].counts + 2, c->survivors.p, c->survivorCount.p, max_depth);
+		// (ENV: the scene has an InfiniteAreaLight, GLASS: a rough-dielectric material -- each instantiation carries only what it needs)
+#define SHADE_B(E, G) k_shade_b<E, G><<<shadeBlocks, AGPT_SHADE_THREADS, 0, c->stream>>>(sc, ps, c->survivors.p, q[cur ^ 1], sp, c->rayCounters.p)
+		if (c->envW > 0) { if (c->hasGlass) SHADE_B(true, true); else SHADE_B(true, false); }
+		else { if (c->hasGlass) SHADE_B(false, true); else SHADE_B(false, false); }
+#undef SHADE_B
 		c->stats.kernel_launches++;
 		c->stats.kernel_launches++; c->stats.launches_shade++;
 		CU(cudaGetLastError());
@@ -1351,27 +1351,27 @@ __global__ void k_probe_bsdf(int n, agpt_material mat, const float* in14, int sk
 	DSurface si;
 	SurfaceInit(si, f3(0.f), dpdu, dpdv);
 	VertexBsdf vb;
-	VertexBsdfInit(vb, si, &mat, wo);
+	VertexBsdfInit<true>(vb, si, &mat, wo);
 	float* o = out12 + 12 * i;
 	// f(wo, wi) and Pdf(wo, wi): zero when wo.z == 0 (reflection.h:117,178)
 	float3 f = f3(0.f);
 	float pdf = 0.f;
 	LobeEval ev;
 	if (vb.woOk) {
-		EvalLobes(vb, WorldToLocal(vb.b, wi), ev);
-		f = FinishEval(vb, ev, wi, &pdf);
+		EvalLobes<true>(vb, WorldToLocal(vb.b, wi), ev);
+		f = FinishEval<true>(vb, ev, wi, &pdf);
 	}
 	o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = pdf;
 	// Sample_f(wo, &wi, u, &pdf, skipSpecular, &sampledSpecular)
 	DirSample smp;
-	SampleLobeDir(vb, u, skipSpecular != 0, smp);
+	SampleLobeDir<true>(vb, u, skipSpecular != 0, smp);
 	float3 wis = f3(0.f), fs = f3(0.f);
 	float pdfs = 0.f;
 	if (smp.ok) {
-		ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
-		if (smp.lobe != AGPT_LOBE_SPECULAR) EvalLobes(vb, smp.wi, ev);
+		ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f; ev.fT = f3(0.f); ev.pdfT = 0.f;
+		if (smp.lobe != AGPT_LOBE_SPECULAR) EvalLobes<true>(vb, smp.wi, ev);
 		wis = LocalToWorld(vb.b, smp.wi);
-		fs = FinishSample(vb, smp, ev, wis, &pdfs);
+		fs = FinishSample<true>(vb, smp, ev, wis, &pdfs);
 	}
 	bool spec = vb.woOk && smp.matching > 0 && smp.lobe == AGPT_LOBE_SPECULAR;
 	o[4] = wis.x; o[5] = wis.y; o[6] = wis.z; o[7] = fs.x; o[8] = fs.y; o[9] = fs.z; o[10] = pdfs; o[11] = spec ? 1.f : 0.f;

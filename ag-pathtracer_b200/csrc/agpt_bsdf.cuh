@@ -154,7 +154,49 @@ __device__ __forceinline__ int LobeList(const agpt_material& m, bool skipSpecula
 	if (m.lobes & AGPT_LOBE_RETRO) lobes[n++] = AGPT_LOBE_RETRO;
 	if (m.lobes & AGPT_LOBE_MICROFACET) lobes[n++] = AGPT_LOBE_MICROFACET;
 	if ((m.lobes & AGPT_LOBE_SPECULAR) && !skipSpecular) lobes[n++] = AGPT_LOBE_SPECULAR;
+	if (m.lobes & AGPT_LOBE_GLASS_REFLECT) lobes[n++] = AGPT_LOBE_GLASS_REFLECT;       // extension (agpt.h)
+	if (m.lobes & AGPT_LOBE_GLASS_TRANSMIT) lobes[n++] = AGPT_LOBE_GLASS_TRANSMIT;
 	return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// EXTENSION: rough dielectric (agpt.h AGPT_LOBE_GLASS_*; CPU statement: oracle/agpt_oracle.cpp GlassT_f / GlassT_Pdf / Refract).
+// The reflection half is the reference's MicrofacetReflection over its plain TrowbridgeReitzDistribution and
+// FresnelDielectric; the transmission half follows PBRT-v3's MicrofacetTransmission (radiance transport).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool Refract(float3 wi, float3 n, float eta, float3* wt) {
+	float cosThetaI = dot(n, wi);
+	float sin2ThetaI = smax(0.f, 1.f - cosThetaI * cosThetaI);
+	float sin2ThetaT = eta * eta * sin2ThetaI;
+	if (sin2ThetaT >= 1) return false;
+	float cosThetaT = sqrtf(1 - sin2ThetaT);
+	*wt = eta * -wi + (eta * cosThetaI - cosThetaT) * n;
+	return true;
+}
+// lambdaO = Lambda(wo), G1o = G1(wo): hoisted per vertex
+__device__ __forceinline__ float GlassT_Pdf(const agpt_material& m, float3 wo, float3 wi, float G1o, float absCosO) {
+	if (SameHemisphere(wo, wi)) return 0;
+	float eta = CosTheta(wo) > 0 ? (m.eta / 1.f) : (1.f / m.eta);
+	float3 wh = normalize(wo + wi * eta);
+	if (dot(wo, wh) * dot(wi, wh) > 0) return 0;
+	float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+	float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+	return TR_D(m.alpha_x, m.alpha_y, wh) * G1o * absdot(wo, wh) / absCosO * dwh_dwi;
+}
+__device__ __forceinline__ float3 GlassT_f(const agpt_material& m, float3 wo, float3 wi, float lambdaO, float lambdaI) {
+	if (SameHemisphere(wo, wi)) return f3(0.f);
+	float cosThetaO = CosTheta(wo), cosThetaI = CosTheta(wi);
+	if (cosThetaI == 0 || cosThetaO == 0) return f3(0.f);
+	float eta = CosTheta(wo) > 0 ? (m.eta / 1.f) : (1.f / m.eta);
+	float3 wh = normalize(wo + wi * eta);
+	if (wh.z < 0) wh = -wh;
+	if (dot(wo, wh) * dot(wi, wh) > 0) return f3(0.f);
+	float F = FrDielectric(dot(wo, wh), 1.f, m.eta);
+	float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+	float factor = 1 / eta;
+	float G = 1 / (1 + lambdaO + lambdaI);
+	return (f3(1.f) - f3(F)) * f3(m.diffuse_r) *
+		fabsf(TR_D(m.alpha_x, m.alpha_y, wh) * G * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor / (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -380,9 +422,12 @@ struct VertexBsdf {
 	DBSDF b;
 	float3 woW, wo;          // outgoing direction, world and shading space
 	float absCosO, Fo, G1o;  // |cos theta_o|, SchlickWeight(|cos theta_o|), G1(wo)
+	float lambdaO;           // Lambda(wo) (GLASS only: the non-separable G of the plain Trowbridge-Reitz distribution)
 	bool woOk;               // wo.z != 0 (BSDF::f / Pdf / Sample_f return 0 otherwise)
-	int nLobes;              // non-specular lobes: diffuse, retro, microfacet
+	int nLobes;              // non-specular lobes: diffuse, retro, microfacet, glass reflection, glass transmission
 };
+// GLASS: the scene has a rough-dielectric material (extension); the instantiation without it carries none of that code.
+template <bool GLASS>
 __device__ __forceinline__ void VertexBsdfInit(VertexBsdf& v, const DSurface& si, const agpt_material* m, float3 woW) {
 	v.b = MakeBSDF(si, m);
 	v.woW = woW;
@@ -390,15 +435,24 @@ __device__ __forceinline__ void VertexBsdfInit(VertexBsdf& v, const DSurface& si
 	v.woOk = v.wo.z != 0;
 	v.absCosO = AbsCosTheta(v.wo);
 	v.Fo = SchlickWeight(v.absCosO);
-	v.G1o = (m->lobes & AGPT_LOBE_MICROFACET) ? TR_G1(m->alpha_x, m->alpha_y, v.wo) : 0.f;
+	v.lambdaO = 0.f;
+	if (GLASS && (m->lobes & (AGPT_LOBE_GLASS_REFLECT | AGPT_LOBE_GLASS_TRANSMIT))) {
+		v.lambdaO = TR_Lambda(m->alpha_x, m->alpha_y, v.wo);
+		v.G1o = 1 / (1 + v.lambdaO);
+	}
+	else v.G1o = (m->lobes & AGPT_LOBE_MICROFACET) ? TR_G1(m->alpha_x, m->alpha_y, v.wo) : 0.f;
 	v.nLobes = ((m->lobes & AGPT_LOBE_DIFFUSE) ? 1 : 0) + ((m->lobes & AGPT_LOBE_RETRO) ? 1 : 0) + ((m->lobes & AGPT_LOBE_MICROFACET) ? 1 : 0);
+	if (GLASS) v.nLobes += ((m->lobes & AGPT_LOBE_GLASS_REFLECT) ? 1 : 0) + ((m->lobes & AGPT_LOBE_GLASS_TRANSMIT) ? 1 : 0);
 }
 
 struct LobeEval {
 	float3 f;          // sum of the non-specular lobes' f(wo, wi) in bxdfs[] order (caller applies `reflect`)
 	float pdfCos;      // BxDF::Pdf of a cosine-sampled lobe (reflection.h:16-18)
-	float pdfMicro;    // MicrofacetReflection::Pdf (reflection.h:67-71)
+	float pdfMicro;    // MicrofacetReflection::Pdf (reflection.h:67-71): the Disney microfacet lobe or the glass reflection lobe
+	float3 fT;         // GLASS: f of the transmission lobe (contributes when wi, wo lie on opposite sides of the geometric normal)
+	float pdfT;        // GLASS: MicrofacetTransmission::Pdf
 };
+template <bool GLASS>
 __device__ __forceinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEval& out) {
 	const agpt_material& m = *v.b.mat;
 	const float absCosI = AbsCosTheta(wi);
@@ -432,11 +486,32 @@ __device__ __forceinline__ void EvalLobes(const VertexBsdf& v, float3 wi, LobeEv
 		}
 		f += fm;
 	}
+	out.fT = f3(0.f); out.pdfT = 0.f;
+	if (GLASS && (m.lobes & (AGPT_LOBE_GLASS_REFLECT | AGPT_LOBE_GLASS_TRANSMIT))) {
+		const float lambdaI = TR_Lambda(m.alpha_x, m.alpha_y, wi);
+		if (m.lobes & AGPT_LOBE_GLASS_REFLECT) {                                                        // reflection.h:42-54,67-71 + microfacet.h:103-105,220-228
+			float3 fr = f3(0.f);
+			if (!(absCosI == 0 || v.absCosO == 0) && !whZero) {
+				float3 F = f3(FrDielectric(dot(wi, Faceforward(wh, f3(0, 0, 1))), 1.f, m.eta));
+				float D = TR_D(m.alpha_x, m.alpha_y, wh);
+				float G = 1 / (1 + v.lambdaO + lambdaI);
+				fr = f3(m.mirror_r) * D * G * F / (4 * absCosI * v.absCosO);
+			}
+			// (MicrofacetReflection::Pdf has no zero-vector check: wh = normalize(wo + wi) as is)
+			if (same) out.pdfMicro = TR_D(m.alpha_x, m.alpha_y, wh) * v.G1o * absdot(v.wo, wh) / v.absCosO / (4 * dot(v.wo, wh));
+			f += fr;
+		}
+		if (m.lobes & AGPT_LOBE_GLASS_TRANSMIT) {
+			out.fT = GlassT_f(m, v.wo, wi, v.lambdaO, lambdaI);
+			out.pdfT = GlassT_Pdf(m, v.wo, wi, v.G1o, v.absCosO);
+		}
+	}
 	out.f = f;
 }
 
 // BSDF::f and BSDF::Pdf of a given world direction from one EvalLobes result (reflection.h:114-123,
 // 174-188; specular lobes contribute nothing to either).  The caller checks v.woOk.
+template <bool GLASS>
 __device__ __forceinline__ float3 FinishEval(const VertexBsdf& v, const LobeEval& e, float3 wiW, float* pdfOut) {
 	const agpt_material& m = *v.b.mat;
 	bool reflect = dot(wiW, v.b.ng) * dot(v.woW, v.b.ng) > 0;
@@ -444,8 +519,10 @@ __device__ __forceinline__ float3 FinishEval(const VertexBsdf& v, const LobeEval
 	if (m.lobes & AGPT_LOBE_DIFFUSE) p += e.pdfCos;
 	if (m.lobes & AGPT_LOBE_RETRO) p += e.pdfCos;
 	if (m.lobes & AGPT_LOBE_MICROFACET) p += e.pdfMicro;
+	if (GLASS && (m.lobes & AGPT_LOBE_GLASS_REFLECT)) p += e.pdfMicro;
+	if (GLASS && (m.lobes & AGPT_LOBE_GLASS_TRANSMIT)) p += e.pdfT;
 	*pdfOut = v.nLobes > 0 ? p / v.nLobes : 0.f;
-	return reflect ? e.f : f3(0.f);
+	return reflect ? e.f : (GLASS ? e.fT : f3(0.f));
 }
 
 struct DirSample {
@@ -457,9 +534,10 @@ struct DirSample {
 	bool ok;          // false where BSDF::Sample_f returns black (reflection.h:130-157)
 };
 // First half of BSDF::Sample_f: choose the lobe, remap u, sample its direction (reflection.h:126-157).
+template <bool GLASS>
 __device__ __forceinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, bool skipSpecular, DirSample& s) {
 	const agpt_material& m = *v.b.mat;
-	int lobes[4];
+	int lobes[6];
 	int matching = LobeList(m, skipSpecular, lobes);
 	s.ok = false; s.pdf = 0; s.lobe = 0; s.matching = matching; s.wi = f3(0.f); s.fSpec = f3(0.f);
 	if (matching == 0) return;
@@ -475,12 +553,19 @@ __device__ __forceinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, boo
 		pdf = 1;
 		s.fSpec = f3(1.f) * f3(m.mirror_r) / AbsCosTheta(wi);
 	}
-	else if (lobe == AGPT_LOBE_MICROFACET) {
+	else if (lobe == AGPT_LOBE_MICROFACET || (GLASS && lobe == AGPT_LOBE_GLASS_REFLECT)) {
 		float3 wh = TR_Sample_wh(m.alpha_x, m.alpha_y, wo, uR);
 		if (!(dot(wo, wh) < 0)) {
 			wi = Reflect(wo, wh);
 			if (SameHemisphere(wo, wi))
 				pdf = TR_D(m.alpha_x, m.alpha_y, wh) * v.G1o * absdot(wo, wh) / v.absCosO / (4 * dot(wo, wh));
+		}
+	}
+	else if (GLASS && lobe == AGPT_LOBE_GLASS_TRANSMIT) {                          // MicrofacetTransmission::Sample_f
+		float3 wh = TR_Sample_wh(m.alpha_x, m.alpha_y, wo, uR);
+		if (!(dot(wo, wh) < 0)) {
+			float eta = CosTheta(wo) > 0 ? (1.f / m.eta) : (m.eta / 1.f);
+			if (Refract(wo, wh, eta, &wi)) pdf = GlassT_Pdf(m, wo, wi, v.G1o, v.absCosO);
 		}
 	}
 	else {
@@ -492,6 +577,7 @@ __device__ __forceinline__ void SampleLobeDir(const VertexBsdf& v, float2 u, boo
 	s.wi = wi; s.pdf = pdf; s.ok = true;
 }
 // Second half of BSDF::Sample_f: overall pdf over the matching lobes and the BSDF value (reflection.h:158-171).
+template <bool GLASS>
 __device__ __forceinline__ float3 FinishSample(const VertexBsdf& v, const DirSample& s, const LobeEval& e, float3 wiW, float* pdfOut) {
 	const agpt_material& m = *v.b.mat;
 	const bool specular = s.lobe == AGPT_LOBE_SPECULAR;
@@ -500,11 +586,13 @@ __device__ __forceinline__ float3 FinishSample(const VertexBsdf& v, const DirSam
 		if ((m.lobes & AGPT_LOBE_DIFFUSE) && s.lobe != AGPT_LOBE_DIFFUSE) pdf += e.pdfCos;
 		if ((m.lobes & AGPT_LOBE_RETRO) && s.lobe != AGPT_LOBE_RETRO) pdf += e.pdfCos;
 		if ((m.lobes & AGPT_LOBE_MICROFACET) && s.lobe != AGPT_LOBE_MICROFACET) pdf += e.pdfMicro;
+		if (GLASS && (m.lobes & AGPT_LOBE_GLASS_REFLECT) && s.lobe != AGPT_LOBE_GLASS_REFLECT) pdf += e.pdfMicro;
+		if (GLASS && (m.lobes & AGPT_LOBE_GLASS_TRANSMIT) && s.lobe != AGPT_LOBE_GLASS_TRANSMIT) pdf += e.pdfT;
 	}
 	if (s.matching > 1) pdf /= s.matching;
 	*pdfOut = pdf;
 	if (specular) return s.fSpec;
 	bool reflect = dot(wiW, v.b.ng) * dot(v.woW, v.b.ng) > 0;
-	return reflect ? e.f : f3(0.f);
+	return reflect ? e.f : (GLASS ? e.fT : f3(0.f));
 }
 

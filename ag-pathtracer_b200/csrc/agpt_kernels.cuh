@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) k_shade_a(DScene sc, PathState ps, const 
 #define AGPT_SHADE_MIN_BLOCKS 1
 #endif
 
-template <bool ENV>
+template <bool ENV, bool GLASS>
 __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_shade_b(DScene sc, PathState ps, const int* __restrict__ survivors, WaveQueues qout, ShadeParams sp, RayCounters* rc) {
 	const int lane = threadIdx.x & 31;
 	const int count = *sp.count;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 		DRay vis;
 		vis.O = f3(0.f); vis.D = f3(0.f); vis.t = 0.f;
 		int lightType = -1, lightPrimType = -1, lightPayload = 0;
-		VertexBsdfInit(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
+		VertexBsdfInit<GLASS>(vb, si, mat, wo);       // cheap enough to run unconditionally (keeps vb defined for idle threads)
 		if (full) {
 			doNee = !BSDF_IsPerfectlySpecular(vb.b) && sc.n_lights > 0;
 			// ---- all RNG draws of this vertex up to the BSDF sample, in the reference's order ----
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			bool want = full && (k == 0 ? doNee : true);
 			if (want) {
 				DirSample s;
-				SampleLobeDir(vb, k == 0 ? uScattering : u, k == 0, s);
+				SampleLobeDir<GLASS>(vb, k == 0 ? uScattering : u, k == 0, s);
 				if (k == 0) smpMis = s; else smpCont = s;
 			}
 		}
@@ -629,15 +629,15 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && sampledLobe != AGPT_LOBE_SPECULAR));
 			float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : sampledWi;
 			LobeEval ev;
-			ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f;
-			if (need) EvalLobes(vb, wiLoc, ev);
+			ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f; ev.fT = f3(0.f); ev.pdfT = 0.f;
+			if (need) EvalLobes<GLASS>(vb, wiLoc, ev);
 			if (k == 0) {
-				if (need) fLight = FinishEval(vb, ev, wiL, &pdfLight);     // BSDF::f and BSDF::Pdf at the light direction
+				if (need) fLight = FinishEval<GLASS>(vb, ev, wiL, &pdfLight);     // BSDF::f and BSDF::Pdf at the light direction
 			}
 			else if (full && sampled) {
 				float3 w = LocalToWorld(vb.b, sampledWi);
 				float p = 0.f;
-				float3 f = FinishSample(vb, k == 1 ? smpMis : smpCont, ev, w, &p);
+				float3 f = FinishSample<GLASS>(vb, k == 1 ? smpMis : smpCont, ev, w, &p);
 				if (k == 1) { wiMis = w; fMis = f; pdfMis = p; } else { wiCont = w; fCont = f; pdfCont = p; }
 			}
 		}

@@ -170,6 +170,7 @@ int agpt_host_make_material(int type, const float* c, float roughness, float met
 	if (!c || !out) return HostFail("null argument");
 	if (type == AGPT_MAT_DISNEY) *out = DisneyMaterial(float3(c[0], c[1], c[2]), roughness, metallic).Export();
 	else if (type == AGPT_MAT_MIRROR) *out = MirrorMaterial(float3(c[0], c[1], c[2])).Export();
+	else if (type == AGPT_MAT_GLASS) *out = GlassMaterial(float3(c[0], c[1], c[2]), float3(c[0], c[1], c[2]), roughness, metallic > 0 ? metallic : 1.5f).Export();   // (Kr = Kt = color; the `metallic` slot carries eta)
 	else return HostFail("unknown material type");
 	return AGPT_OK;
 }

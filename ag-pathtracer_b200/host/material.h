@@ -64,3 +64,29 @@ public:
 private:
 	agpt_material rec;
 };
+
+// EXTENSION (not a reference class): a rough dielectric interface as PBRT-v3's GlassMaterial builds
+// it -- MicrofacetReflection(Kr, TrowbridgeReitz(alpha), FresnelDielectric(1, eta)), which the reference's own classes
+// can express (reflection.h:38-78, microfacet.h:112-153,220-228), plus MicrofacetTransmission(Kt, ...), which they
+// cannot.  alpha = max(.001, roughness^2) like DisneyMaterial (material.h:39-41).  transmit = false keeps the
+// reflection lobe alone (the half that can be checked against the reference).  See include/agpt.h AGPT_LOBE_GLASS_*.
+#define AGPT_HAS_GLASS 1
+class GlassMaterial : public Material {
+public:
+	GlassMaterial(const float3& Kr, const float3& Kt, float roughness, float eta = 1.5f, bool transmit = true) {
+		memset(&rec, 0, sizeof(rec));
+		rec.type = AGPT_MAT_GLASS;
+		rec.lobes = AGPT_LOBE_GLASS_REFLECT | (transmit ? AGPT_LOBE_GLASS_TRANSMIT : 0);
+		rec.roughness = roughness;
+		rec.eta = eta;
+		rec.mirror_r[0] = Kr.x; rec.mirror_r[1] = Kr.y; rec.mirror_r[2] = Kr.z;
+		rec.diffuse_r[0] = Kt.x; rec.diffuse_r[1] = Kt.y; rec.diffuse_r[2] = Kt.z;
+		rec.alpha_x = rec.alpha_y = std::max(0.001f, std::max(.001f, sqr(roughness)));
+	}
+	agpt_material Export() const override { return rec; }
+	static std::shared_ptr<GlassMaterial> Make(const float3& Kr, const float3& Kt, float roughness, float eta = 1.5f, bool transmit = true) {
+		return std::make_shared<GlassMaterial>(Kr, Kt, roughness, eta, transmit);
+	}
+private:
+	agpt_material rec;
+};

@@ -42,6 +42,7 @@ inline ConfigDefaults Defaults(int config) {
 	case 7: return { 400, 400, 64, 5, 0, "cfg7_reference_default_scene_envmap_400x400" };
 	case 8: return { 640, 360, 16, 6, 4, "cfg8_test_degenerate_triangles_deep_tree_overflowing_light" };
 	case 9: return { 3840, 2160, 1024, 8, 0, "cfg9_ext_cfg4_with_true_instances_one_mesh_8_placements" };
+	case 10: return { 1920, 1080, 64, 16, 0, "cfg10_ext_cfg5_rough_glass_rr_by_bounce" };
 	default: return { 0, 0, 0, 0, 0, "unknown" };
 	}
 }
@@ -498,6 +499,31 @@ inline void BuildConfig9(Scene* scene, int level) {
 }
 #endif
 
+#ifdef AGPT_HAS_GLASS
+// cfg 10 (EXTENSION, host mirror only -- the reference has no transmission lobe): BASELINE config 5 as its wording has
+// it, "rough-glass plus diffuse interreflection, 16 bounces with Russian roulette": cfg 5's closed room with the rough
+// metal icosphere replaced by ROUGH GLASS (roughness .3, eta 1.5); meant to be rendered with AGPT_FLAG_RR_BY_BOUNCE.
+inline void BuildConfig10(Scene* scene, int level) {
+	auto wall = DisneyMaterial::Make(float3(.73f, .73f, .73f), 1.f, 0.f);
+	auto room = MakeRoom(float3(-4, -1, -9), float3(4, 5, 4), wall);
+	scene->primitives.push_back(std::make_shared<BVHTriMesh>(room, wall, 1));
+	auto glass = GlassMaterial::Make(float3(1.f, 1.f, 1.f), float3(.95f, .97f, 1.f), .3f, 1.5f);
+	auto diffuse = DisneyMaterial::Make(float3(.2f, .45f, .7f), 1.f, 0.f);
+	auto a = MakeIcosphere(level, float3(-1.4f, .2f, .5f), 1.2f, glass);
+	auto b = MakeIcosphere(level, float3(1.4f, .2f, -.5f), 1.2f, diffuse);
+	scene->primitives.push_back(std::make_shared<BVHTriMesh>(a, glass, 1));
+	scene->primitives.push_back(std::make_shared<BVHTriMesh>(b, diffuse, 1));
+	scene->primitives.push_back(std::make_shared<Sphere>(float3(0.f, -.4f, -2.5f), .6f, GlassMaterial::Make(float3(1.f, 1.f, 1.f), float3(1.f, .9f, .8f), .05f, 1.33f)));
+	scene->addAreaLight(std::make_shared<Sphere>(float3(0, 4.2f, -1.f), .4f, nullptr), WarmWhite(15));
+	scene->camera.lookfrom = float3(0, 1.8f, -8.5f);
+	scene->camera.lookat = float3(0, .6f, 0);
+	scene->camera.vup = float3(0, 1, 0);
+	scene->camera.aspect_ratio = 16.f / 9.f;
+	scene->camera.vfov = 40;
+	scene->camera.aperture = 0;
+}
+#endif
+
 // level <= 0 selects the BASELINE.json size of each configuration.
 inline bool BuildConfig(Scene* scene, int config, int level) {
 	switch (config) {
@@ -511,6 +537,9 @@ inline bool BuildConfig(Scene* scene, int config, int level) {
 	case 8: BuildConfig8(scene, level > 0 ? level : 3); return true;
 #ifdef AGPT_HAS_INSTANCES
 	case 9: BuildConfig9(scene, level > 0 ? level : 8); return true;
+#endif
+#ifdef AGPT_HAS_GLASS
+	case 10: BuildConfig10(scene, level > 0 ? level : 7); return true;
 #endif
 	default: return false;
 	}

@@ -106,8 +106,16 @@ typedef struct agpt_prim {
 	                        `prim` must be this row (one shape per AreaLight, as upstream), else AGPT_ERR_INVALID */
 } agpt_prim;
 
-enum { AGPT_MAT_DISNEY = 1, AGPT_MAT_MIRROR = 2 };
-enum { AGPT_LOBE_DIFFUSE = 1, AGPT_LOBE_RETRO = 2, AGPT_LOBE_MICROFACET = 4, AGPT_LOBE_SPECULAR = 8 };
+enum { AGPT_MAT_DISNEY = 1, AGPT_MAT_MIRROR = 2, AGPT_MAT_GLASS = 3 /* EXTENSION: rough dielectric */ };
+enum { AGPT_LOBE_DIFFUSE = 1, AGPT_LOBE_RETRO = 2, AGPT_LOBE_MICROFACET = 4, AGPT_LOBE_SPECULAR = 8,
+       /* EXTENSION (BASELINE config 5 says "rough-glass"): a rough dielectric interface as PBRT-v3's GlassMaterial
+        * builds it.  GLASS_REFLECT is the reference's own MicrofacetReflection (reflection.h:38-78) over its plain
+        * TrowbridgeReitzDistribution (G = 1/(1 + Lambda(wo) + Lambda(wi)), microfacet.h:103-105) and its FresnelDielectric(1, eta)
+        * (microfacet.h:220-228).  GLASS_TRANSMIT -- MicrofacetTransmission (PBRT-v3 reflection.cpp, radiance transport) -- and the
+        * rule that a transmission lobe contributes to BSDF::f when wi and wo lie on opposite sides of the geometric normal do not
+        * exist upstream (its BSDF::f only sums when both lie on the same side, reflection.h:114-123): parity for those is against
+        * oracle/agpt_oracle.cpp only.  bxdfs[] order: GLASS_REFLECT, GLASS_TRANSMIT. */
+       AGPT_LOBE_GLASS_REFLECT = 16, AGPT_LOBE_GLASS_TRANSMIT = 32 };
 
 /* Constants the reference's material constructors derive once (material.h:14-49,74-77). */
 typedef struct agpt_material {
@@ -115,11 +123,11 @@ typedef struct agpt_material {
 	uint32_t lobes;       /* AGPT_LOBE_* in BSDF::bxdfs[] order: diffuse, retro, microfacet | specular */
 	float roughness;      /* DisneyRetro::roughness */
 	float metallic;       /* DisneyFresnel::metallic */
-	float diffuse_r[3];   /* (1-metallic)*color: R of DisneyDiffuse and DisneyRetro */
+	float diffuse_r[3];   /* (1-metallic)*color: R of DisneyDiffuse and DisneyRetro; GLASS: T of the transmission lobe */
 	float eta;            /* 1.5 (material.h:65) */
 	float spec_r0[3];     /* DisneyFresnel::R0 = Lerp(metallic, SchlickR0FromEta(eta), color) */
 	float alpha_x;        /* max(.001, roughness^2) */
-	float mirror_r[3];    /* SpecularReflection::R */
+	float mirror_r[3];    /* SpecularReflection::R; GLASS: R of the reflection lobe */
 	float alpha_y;
 } agpt_material;
 

@@ -490,7 +490,54 @@ V3 TR_Sample_wh(const agpt_material& m, V3 wo, float u0, float u1) {            
 	return wh;
 }
 
+// ---- EXTENSION: rough dielectric (agpt.h AGPT_LOBE_GLASS_*) ---------------------------------
+inline float TR_G(const agpt_material& m, V3 wo, V3 wi) { return 1 / (1 + TR_Lambda(m, wo) + TR_Lambda(m, wi)); }     // microfacet.h:103-105
+// PBRT-v3 Refract(wi, n, eta, wt): false on total internal reflection
+inline bool Refract(V3 wi, V3 n, float eta, V3* wt) {
+	float cosThetaI = dot(n, wi);
+	float sin2ThetaI = std::max(0.f, 1.f - cosThetaI * cosThetaI);
+	float sin2ThetaT = eta * eta * sin2ThetaI;
+	if (sin2ThetaT >= 1) return false;
+	float cosThetaT = std::sqrt(1 - sin2ThetaT);
+	*wt = eta * -wi + (eta * cosThetaI - cosThetaT) * n;
+	return true;
+}
+// MicrofacetTransmission::f / Pdf (PBRT-v3 reflection.cpp), etaA = 1 outside, etaB = m.eta inside, TransportMode::Radiance
+V3 GlassT_f(const agpt_material& m, V3 wo, V3 wi) {
+	if (SameHemisphere(wo, wi)) return v3(0.f);
+	float cosThetaO = CosTheta(wo), cosThetaI = CosTheta(wi);
+	if (cosThetaI == 0 || cosThetaO == 0) return v3(0.f);
+	float eta = CosTheta(wo) > 0 ? (m.eta / 1.f) : (1.f / m.eta);
+	V3 wh = normalize(wo + wi * eta);
+	if (wh.z < 0) wh = -wh;
+	if (dot(wo, wh) * dot(wi, wh) > 0) return v3(0.f);
+	float F = FrDielectric(dot(wo, wh), 1.f, m.eta);
+	float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+	float factor = 1 / eta;
+	return (v3(1.f) - v3(F)) * v3(m.diffuse_r) *
+		std::abs(TR_D(m, wh) * TR_G(m, wo, wi) * eta * eta * absdot(wi, wh) * absdot(wo, wh) * factor * factor / (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
+}
+float GlassT_Pdf(const agpt_material& m, V3 wo, V3 wi) {
+	if (SameHemisphere(wo, wi)) return 0;
+	float eta = CosTheta(wo) > 0 ? (m.eta / 1.f) : (1.f / m.eta);
+	V3 wh = normalize(wo + wi * eta);
+	if (dot(wo, wh) * dot(wi, wh) > 0) return 0;
+	float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+	float dwh_dwi = std::abs((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+	return TR_Pdf(m, wo, wh) * dwh_dwi;
+}
+
 V3 Lobe_f(const agpt_material& m, int lobe, V3 wo, V3 wi) {
+	if (lobe == AGPT_LOBE_GLASS_TRANSMIT) return GlassT_f(m, wo, wi);
+	if (lobe == AGPT_LOBE_GLASS_REFLECT) {                                                // reflection.h:42-54 with FresnelDielectric and the base-class G
+		float cosThetaO = AbsCosTheta(wo), cosThetaI = AbsCosTheta(wi);
+		V3 wh = wi + wo;
+		if (cosThetaI == 0 || cosThetaO == 0) return v3(0.f);
+		if (wh.x == 0 && wh.y == 0 && wh.z == 0) return v3(0.f);
+		wh = normalize(wh);
+		V3 F = v3(FrDielectric(dot(wi, Faceforward(wh, v3(0, 0, 1))), 1.f, m.eta));
+		return v3(m.mirror_r) * TR_D(m, wh) * TR_G(m, wo, wi) * F / (4 * cosThetaI * cosThetaO);
+	}
 	if (lobe == AGPT_LOBE_DIFFUSE) {                                                      // disney.h:27-34
 		float Fo = SchlickWeight(AbsCosTheta(wo)), Fi = SchlickWeight(AbsCosTheta(wi));
 		return v3(m.diffuse_r) * kInvPi * (1 - Fo / 2) * (1 - Fi / 2);
@@ -518,7 +565,8 @@ V3 Lobe_f(const agpt_material& m, int lobe, V3 wo, V3 wi) {
 }
 float Lobe_Pdf(const agpt_material& m, int lobe, V3 wo, V3 wi) {
 	if (lobe == AGPT_LOBE_DIFFUSE || lobe == AGPT_LOBE_RETRO) return SameHemisphere(wo, wi) ? AbsCosTheta(wi) * kInvPi : 0;   // reflection.h:16-18
-	if (lobe == AGPT_LOBE_MICROFACET) {                                                   // reflection.h:67-71
+	if (lobe == AGPT_LOBE_GLASS_TRANSMIT) return GlassT_Pdf(m, wo, wi);
+	if (lobe == AGPT_LOBE_MICROFACET || lobe == AGPT_LOBE_GLASS_REFLECT) {                // reflection.h:67-71
 		if (!SameHemisphere(wo, wi)) return 0;
 		V3 wh = normalize(wo + wi);
 		return TR_Pdf(m, wo, wh) / (4 * dot(wo, wh));
@@ -537,7 +585,12 @@ struct Bsdf {                                                                   
 		if (m->lobes & AGPT_LOBE_RETRO) lobes[nAll++] = AGPT_LOBE_RETRO;
 		if (m->lobes & AGPT_LOBE_MICROFACET) lobes[nAll++] = AGPT_LOBE_MICROFACET;
 		if (m->lobes & AGPT_LOBE_SPECULAR) lobes[nAll++] = AGPT_LOBE_SPECULAR;
+		if (m->lobes & AGPT_LOBE_GLASS_REFLECT) lobes[nAll++] = AGPT_LOBE_GLASS_REFLECT;      // extension
+		if (m->lobes & AGPT_LOBE_GLASS_TRANSMIT) lobes[nAll++] = AGPT_LOBE_GLASS_TRANSMIT;
 	}
+	// which lobes BSDF::f sums for a pair of directions: reflection lobes when wi, wo lie on the same side of the geometric
+	// normal (reflection.h:118-121); a transmission lobe -- extension -- when they lie on opposite sides (PBRT-v3 BSDF::f)
+	static bool Contributes(int lobe, bool reflect) { return lobe == AGPT_LOBE_GLASS_TRANSMIT ? !reflect : reflect; }
 	static bool Matches(int lobe, bool skipSpecular) { return !skipSpecular || lobe != AGPT_LOBE_SPECULAR; }
 	bool IsPerfectlySpecular() const { for (int i = 0; i < nAll; i++) if (lobes[i] != AGPT_LOBE_SPECULAR) return false; return true; }
 	V3 ToLocal(V3 v) const { return v3(dot(v, ss), dot(v, ts), dot(v, ns)); }
@@ -550,7 +603,7 @@ struct Bsdf {                                                                   
 		bool reflect = dot(wiW, ng) * dot(woW, ng) > 0;
 		V3 r = v3(0.f);
 		for (int i = 0; i < nAll; i++)
-			if (Matches(lobes[i], skipSpecular) && reflect) r += Lobe_f(*m, lobes[i], wo, wi);
+			if (Matches(lobes[i], skipSpecular) && Contributes(lobes[i], reflect)) r += Lobe_f(*m, lobes[i], wo, wi);
 		return r;
 	}
 	float Pdf(V3 woW, V3 wiW, bool skipSpecular) const {
@@ -583,11 +636,18 @@ struct Bsdf {                                                                   
 			*pdf = 1;
 			f = v3(1.f) * v3(m->mirror_r) / AbsCosTheta(wi);
 		}
-		else if (lobe == AGPT_LOBE_MICROFACET) {                                          // reflection.h:55-66
+		else if (lobe == AGPT_LOBE_MICROFACET || lobe == AGPT_LOBE_GLASS_REFLECT) {       // reflection.h:55-66
 			V3 wh = TR_Sample_wh(*m, wo, ur0, ur1);
 			if (!(dot(wo, wh) < 0)) {
 				wi = Reflect(wo, wh);
 				if (SameHemisphere(wo, wi)) *pdf = TR_Pdf(*m, wo, wh) / (4 * dot(wo, wh));
+			}
+		}
+		else if (lobe == AGPT_LOBE_GLASS_TRANSMIT) {                                      // MicrofacetTransmission::Sample_f (PBRT-v3)
+			V3 wh = TR_Sample_wh(*m, wo, ur0, ur1);
+			if (!(dot(wo, wh) < 0)) {
+				float eta = CosTheta(wo) > 0 ? (1.f / m->eta) : (m->eta / 1.f);
+				if (Refract(wo, wh, eta, &wi)) *pdf = GlassT_Pdf(*m, wo, wi);
 			}
 		}
 		else {                                                                            // reflection.h:8-15, common.h:118-143
@@ -614,7 +674,7 @@ struct Bsdf {                                                                   
 			bool reflect = dot(*wiW, ng) * dot(woW, ng) > 0;
 			f = v3(0.f);
 			for (int i = 0; i < nAll; i++)
-				if (Matches(lobes[i], skipSpecular) && reflect) f += Lobe_f(*m, lobes[i], wo, wi);
+				if (Matches(lobes[i], skipSpecular) && Contributes(lobes[i], reflect)) f += Lobe_f(*m, lobes[i], wo, wi);
 		}
 		return f;
 	}
@@ -1023,6 +1083,27 @@ void agpt_oracle_li_pixels(void* h, int W, int H, int n, const int* xs, const in
 		V3 clr = Li(sc, ray, max_depth, depth_arg, rng, c);
 		out_rgb[3 * i] = clr.x; out_rgb[3 * i + 1] = clr.y; out_rgb[3 * i + 2] = clr.z;
 		if (draws_out) draws_out[i] = rng.draws;
+	}
+}
+
+// BSDF::f / Pdf / Sample_f on a flat frame built from (dpdu, dpdv): same contract as agpt_ref_probe_bsdf
+// (oracle/ref_harness.cpp) and agpt_probe_bsdf (include/agpt.h), for a material RECORD.
+void agpt_oracle_probe_bsdf(int n, const agpt_material* mat, const float* in14, int skip_specular, float* out12) {
+	for (int i = 0; i < n; i++) {
+		const float* a = in14 + 14 * i;
+		V3 dpdu = v3(a[0], a[1], a[2]), dpdv = v3(a[3], a[4], a[5]), wo = v3(a[6], a[7], a[8]), wi = v3(a[9], a[10], a[11]);
+		Surface si;
+		si.Init(v3(0.f), dpdu, dpdv);
+		Bsdf bsdf(si, mat);
+		float* o = out12 + 12 * i;
+		V3 f = bsdf.f(wo, wi, skip_specular != 0);
+		o[0] = f.x; o[1] = f.y; o[2] = f.z;
+		o[3] = bsdf.Pdf(wo, wi, skip_specular != 0);
+		V3 wis = v3(0.f);
+		float pdf = 0;
+		bool spec = false;
+		V3 fs = bsdf.Sample_f(wo, &wis, a[12], a[13], &pdf, skip_specular != 0, &spec);
+		o[4] = wis.x; o[5] = wis.y; o[6] = wis.z; o[7] = fs.x; o[8] = fs.y; o[9] = fs.z; o[10] = pdf; o[11] = spec ? 1.f : 0.f;
 	}
 }
 

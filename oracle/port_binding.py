@@ -116,6 +116,14 @@ class PortScene:
         return out, draws
 
 
+def probe_bsdf(material, in14, skip_specular):
+    """BSDF::f / Pdf / Sample_f of the restatement for an agpt_material record (ctypes struct)."""
+    in14 = np.ascontiguousarray(in14, np.float32).reshape(-1, 14)
+    out = np.zeros((len(in14), 12), np.float32)
+    lib().agpt_oracle_probe_bsdf(c_int(len(in14)), ctypes.byref(material), _fp(in14), c_int(1 if skip_specular else 0), _fp(out))
+    return out
+
+
 def probe_stream(pixel, sample, k):
     out = np.zeros(k, np.float32)
     lib().agpt_oracle_probe_stream(c_uint(pixel), c_uint(sample), c_int(k), _fp(out))

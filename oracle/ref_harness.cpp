@@ -416,6 +416,21 @@ void agpt_ref_probe_bounds(int n, const float* boxes6, const float* rays7, int* 
 	}
 }
 
+// The reflection half of the rough-dielectric extension, built from the reference's OWN classes: MicrofacetReflection
+// (reflection.h:38-78) over the plain TrowbridgeReitzDistribution (microfacet.h:112-153) and FresnelDielectric(1, eta)
+// (microfacet.h:220-228).  The reference never combines them (its only Fresnel in use is DisneyFresnel), but it can:
+// this pins AGPT_LOBE_GLASS_REFLECT to reference code.  alpha = max(.001, roughness^2) as host/material.h GlassMaterial.
+class RefGlassReflection : public Material {
+public:
+	RefGlassReflection(const float3& Kr, float roughness, float eta) {
+		float a = std::max(.001f, roughness * roughness);
+		lobe = std::make_shared<MicrofacetReflection>(Kr, new TrowbridgeReitzDistribution(a, a), new FresnelDielectric(1.f, eta));
+	}
+	void SetupBSDF(BSDF* bsdf) const override { bsdf->AddBxDF(lobe.get()); }
+private:
+	std::shared_ptr<MicrofacetReflection> lobe;
+};
+
 // BSDF probe on a flat shading frame.  For each i: builds a SurfaceInteraction from
 // (p=0, dpdu, dpdv), optionally SetShadingGeometry(ss, ts), sets up the material's BSDF and
 // evaluates f(wo,wi,skipSpecular), Pdf, and Sample_f(wo,u).
@@ -424,6 +439,7 @@ void agpt_ref_probe_bounds(int n, const float* boxes6, const float* rays7, int* 
 void agpt_ref_probe_bsdf(int n, const float* mat6, const float* in14, int skip_specular, float* out12) {
 	std::shared_ptr<Material> m;
 	if ((int)mat6[0] == 1) m = DisneyMaterial::Make(float3(mat6[1], mat6[2], mat6[3]), mat6[4], mat6[5]);
+	else if ((int)mat6[0] == 3) m = std::make_shared<RefGlassReflection>(float3(mat6[1], mat6[2], mat6[3]), mat6[4], mat6[5]);   // {3, Kr xyz, roughness, eta}
 	else m = MirrorMaterial::Make(float3(mat6[1], mat6[2], mat6[3]));
 	Sphere shape(float3(0.f), 1.f, m);
 	for (int i = 0; i < n; i++) {

@@ -150,11 +150,39 @@ def function_fixture():
     print("functions.npz: bounds hit rate", d["bounds_hit"].mean())
 
 
+def glass_reflect_fixture():
+    """The reflection lobe of the rough-dielectric extension from the reference's own MicrofacetReflection +
+    TrowbridgeReitzDistribution + FresnelDielectric (oracle/ref_harness.cpp RefGlassReflection): f, Pdf, Sample_f."""
+    rng = np.random.RandomState(23)
+    mats = np.array([[3, 1., 1., 1., .3, 1.5], [3, .9, .8, .7, .05, 1.33], [3, 1., 1., 1., .8, 2.4]], np.float32)      # {3, Kr, roughness, eta}
+    m = 512
+    def unit(v):
+        return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    dpdu = rng.normal(size=(m, 3)).astype(np.float32)
+    dpdv = rng.normal(size=(m, 3)).astype(np.float32)
+    nrm = unit(np.cross(dpdu, dpdv))
+    wo = unit(rng.normal(size=(m, 3)) + 1.5 * nrm)
+    back = rng.rand(m) < 0.3
+    wo[back] = -wo[back]                       # from inside the medium too
+    wi = unit(rng.normal(size=(m, 3)) + 1.0 * nrm)
+    flip = rng.rand(m) < 0.3
+    wi[flip] = -wi[flip]
+    u = rng.rand(m, 2).astype(np.float32)
+    in14 = np.concatenate([dpdu, dpdv, wo, wi, u], 1).astype(np.float32)
+    d = {"mats": mats, "in": in14, "out": np.stack([ref.probe_bsdf(mm, in14, False) for mm in mats])}
+    np.savez_compressed(os.path.join(OUT, "glass_reflect.npz"), **d)
+    print("glass_reflect.npz: nonzero f rows", (np.abs(d["out"][..., :3]).sum(-1) > 0).mean())
+
+
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first (make -C oracle ref)"
+    if sys.argv[1:] == ["glass"]:
+        glass_reflect_fixture()
+        sys.exit(0)
     only = [int(a) for a in sys.argv[1:]]          # e.g. `make_golden.py 8` regenerates scene_cfg8.npz alone
     for case in CASES:
         if not only or case[0] in only:
             scene_fixture(*case)
     if not only:
         function_fixture()
+        glass_reflect_fixture()

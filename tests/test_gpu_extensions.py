@@ -134,3 +134,44 @@ def test_russian_roulette_by_bounce(agpt, port, gpu_ctx):
     ps.set_rr_by_bounce(True)
     want_li, _ = ps.li_pixels(W, H, xs, ys, ss, 16, 0)
     assert np.all(bits(li) == bits(want_li), axis=1).mean() >= 0.97
+
+
+def test_glass_bsdf_against_reference_classes_and_cpu_statement(agpt, port, gpu_ctx):
+    """Rough dielectric: the reflection lobe against golden vectors from the reference's own MicrofacetReflection +
+    TrowbridgeReitzDistribution + FresnelDielectric; reflection + transmission against the CPU statement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glass_reflect.npz"))
+    exact = total = 0
+    for mat6, want in zip(g["mats"], g["out"]):
+        m = agpt.make_material(agpt.MAT_GLASS, mat6[1:4], float(mat6[4]), float(mat6[5]))
+        full = port.probe_bsdf(m, g["in"], False)
+        got_full = gpu_ctx.probe_bsdf(m, g["in"], False)
+        assert np.array_equal(bits(got_full[:, :4]), bits(full[:, :4])), "f / Pdf with the transmission lobe"
+        assert np.isclose(got_full[:, 4:11], full[:, 4:11], rtol=2e-6, atol=1e-7).all()
+        exact += int(np.all(bits(got_full) == bits(full), axis=1).sum()); total += len(full)
+        m.lobes = agpt.LOBE_GLASS_REFLECT
+        got = gpu_ctx.probe_bsdf(m, g["in"], False)
+        assert np.array_equal(bits(got[:, :4]), bits(want[:, :4])), "reflection lobe: f / Pdf of the reference's classes"
+        assert np.isclose(got[:, 4:11], want[:, 4:11], rtol=2e-6, atol=1e-7).all()
+        exact += int(np.all(bits(got) == bits(want), axis=1).sum()); total += len(want)
+    print(f"glass probe rows bit-identical: {exact}/{total}")
+    assert exact / total > 0.995
+
+
+def test_rough_glass_scene_matches_cpu_statement(agpt, port, gpu_ctx):
+    """cfg 10 = BASELINE config 5 as worded: rough glass + diffuse interreflection, 16 bounces, roulette by bounce."""
+    level, W, H, spp = 3, 192, 108, 6
+    d = agpt.config_defaults(10)
+    hs = agpt.HostScene(10, level); ps = port.PortScene(hs)
+    ps.set_rr_by_bounce(True)
+    hs.upload(gpu_ctx); gpu_ctx.set_film(W, H); gpu_ctx.clear(); gpu_ctx.reset_stats()
+    gpu_ctx.render(0, spp, d["max_depth"], 0, agpt.FLAG_RR_BY_BOUNCE)
+    got = gpu_ctx.read_accum()
+    st = gpu_ctx.stats()
+    want, cnt = ps.render(W, H, 0, spp, d["max_depth"], 0)
+    exact = np.all(bits(got[..., :3]) == bits(want[..., :3]), axis=-1).mean()
+    print(f"cfg10: bit-identical pixels {exact:.5f}")
+    assert exact >= 0.999
+    assert st.rays_shadow == cnt["rays_any"]
+    assert st.rays_closest + st.rays_mis + st.rays_mis_culled + st.rays_tail_culled == cnt["rays_closest"]
+    assert np.isfinite(got).all() and got[..., :3].min() >= 0
