@@ -76,6 +76,8 @@ struct agpt_ctx {
 	bool hasGlass = false;        // some material is a rough dielectric (extension): shade runs the GLASS instantiation
 	DevBuf<int> sphereRun;
 	DevBuf<float4> sphereRunBox;
+	DevBuf<float4> keyBoxes;         // root boxes of the meshes that do not cover the scene (ray-bucket key)
+	std::vector<agpt_bvh_node> hostRoots;   // node 0 of every mesh (count < 0: the mesh has no BVH)
 	std::vector<agpt_sphere> hostSpheres;
 	bool runsDirty = true;
 	int maxSphereRun = 1 << 20;   // AGPT_MAX_SPHERE_RUN
@@ -168,6 +170,26 @@ static int BuildSphereRuns(agpt_ctx* c) {
 		b[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
 		b[2] = make_float4(ctr[0], ctr[1], ctr[2], 1.0e4f * rmin * rmin - diag2);
 	}
+	// ray-bucket key: the root boxes of BVH mesh primitives that are small against the union of all of them
+	{
+		std::vector<float4> kb;
+		float lo[3] = { 1e30f, 1e30f, 1e30f }, hi[3] = { -1e30f, -1e30f, -1e30f };
+		std::vector<int> meshPrims;
+		for (int p = 0; p < n; p++)
+			if (rows[p].type == AGPT_PRIM_BVH_MESH && rows[p].payload >= 0 && rows[p].payload < (int)c->hostRoots.size() && c->hostRoots[rows[p].payload].count >= 0) {
+				meshPrims.push_back(rows[p].payload);
+				for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], c->hostRoots[rows[p].payload].bmin[a]); hi[a] = fmaxf(hi[a], c->hostRoots[rows[p].payload].bmax[a]); }
+			}
+		double all = 1;
+		for (int a = 0; a < 3; a++) all *= fmax((double)hi[a] - lo[a], 1e-30);
+		for (int m : meshPrims) {
+			const agpt_bvh_node& r = c->hostRoots[m];
+			double v = 1;
+			for (int a = 0; a < 3; a++) v *= fmax((double)r.bmax[a] - r.bmin[a], 1e-30);
+			if (v <= 0.25 * all && kb.size() < 2 * 16) { kb.push_back(make_float4(r.bmin[0], r.bmin[1], r.bmin[2], r.bmax[0])); kb.push_back(make_float4(r.bmax[1], r.bmax[2], 0.f, 0.f)); }
+		}
+		CU(c->keyBoxes.Upload(kb.data(), kb.size(), c->stream));
+	}
 	CU(c->sphereRun.Upload(run.data(), (size_t)n, c->stream));
 	CU(c->sphereRunBox.Upload(box.data(), box.size(), c->stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -181,6 +203,7 @@ static void SetBucketGrid(DScene& s, const float* lo, const float* hi) {
 
 static DScene MakeScene(const agpt_ctx* c) {
 	DScene s;
+	s.keyBoxes = c->keyBoxes.p; s.n_keyBoxes = (int)(c->keyBoxes.n / 2);
 	s.prims = c->prims.p; s.sphereRun = c->sphereRun.p; s.sphereRunBox = c->sphereRunBox.p; s.spheres = c->spheres.p; s.planes = c->planes.p; s.meshes = c->meshes.p; s.instances = c->instances.p;
 	s.mats = c->mats.p; s.lights = c->lights.p;
 	s.n_prims = (int)c->prims.n; s.n_lights = (int)c->lights.n;
@@ -350,7 +373,7 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	for (int r = 0; r < c->peerWorld; r++) if (r != c->peerRank && c->peerAccum[r]) cudaIpcCloseMemHandle(c->peerAccum[r]);
 	for (auto& m : c->meshStore) m.Free();
-	c->meshes.Free(); c->instances.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->mats.Free(); c->lights.Free();
+	c->meshes.Free(); c->instances.Free(); c->spheres.Free(); c->planes.Free(); c->prims.Free(); c->sphereRun.Free(); c->sphereRunBox.Free(); c->keyBoxes.Free(); c->mats.Free(); c->lights.Free();
 	c->accumOwn.Free(); c->resolved.Free();
 	c->envRgb.Free(); c->envFunc.Free(); c->envCdf.Free();
 	for (auto& b : c->f4) b.Free();
@@ -464,6 +487,9 @@ int agpt_upload_meshes(agpt_ctx* c, const agpt_mesh_desc* meshes, int n) {
 	CU(cudaStreamSynchronize(c->stream));
 	c->nMeshes = n;
 	c->maxBvhDepth = maxDepth;
+	c->hostRoots.assign((size_t)n, agpt_bvh_node());
+	for (int i = 0; i < n; i++) { if (meshes[i].n_nodes > 0) c->hostRoots[i] = meshes[i].nodes[0]; else c->hostRoots[i].count = -1; }
+	c->runsDirty = true;
 	bool any = false;
 	for (int i = 0; i < n; i++) {
 		if (meshes[i].n_nodes == 0) continue;

@@ -62,6 +62,8 @@ struct DScene {
 	float envFuncInt;
 	int envW, envH;
 	float cellLo[3], cellScale[3];   // ray-bucket grid over the bounded geometry: cell = (p - lo) * scale
+	const float4* keyBoxes;          // ray-bucket key: root boxes of the meshes that do NOT cover the scene (2 x float4: min.xyz,max.x | max.yz,-,-)
+	int n_keyBoxes;
 	agpt_camera cam;
 };
 

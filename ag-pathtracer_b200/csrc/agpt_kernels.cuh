@@ -49,9 +49,6 @@ struct PathState {
 	int slots;                      // allocated path slots (debug checks)
 };
 
-#ifndef AGPT_STEEP_BIT
-#define AGPT_STEEP_BIT 1
-#endif
 #ifndef AGPT_CELL_BITS
 #define AGPT_CELL_BITS 3
 #endif
@@ -70,12 +67,31 @@ struct RayCounters {     // device-side totals, see agpt_stats
 	unsigned long long rays_closest, rays_shadow, rays_mis, rays_skip, rays_mis_culled, rays_tail_culled;
 };
 
-// Ray bucket: rays that leave the same primitive in the same direction octant walk similar parts
-// of the trees in the same near/far order, so putting them next to each other in the queue
-// raises both the SIMT efficiency of the lockstep walk and the L1/L2 hit rate.
-// Direction code: the octant (0..7), or for a shadow ray aimed at an area light 8 + (light & 7) --
-// rays from one cell to one small light are as alike as rays get.
-__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, int areaLight = -1, bool steep = false) {
+// Ray bucket: rays that start in the same cell and go the same way walk similar parts of the trees in the same
+// near/far order, so putting them next to each other in the queue raises both the SIMT efficiency of the
+// lockstep walk and the L1/L2 hit rate.  Key = 9 bits Morton cell of the origin | 4 bits direction code:
+//   closest-hit queue (path and MIS rays): octant (3 bits) | "meets the root box of a mesh" (1 bit);
+//   shadow ray to an area light:           8 | light & 3 (2 bits) | "meets ..." (1 bit) -- rays from one cell to
+//                                          one small light are as alike as rays get;
+//   shadow ray to an infinite light:       octant.
+// The "meets" bit (round 2) separates rays that will walk a tree for tens of steps from rays that are done with
+// the mesh run at once -- it is lanes finishing at very different times, not memory, that limits the walk
+// (13.8 of 32 rays alive per step).  It replaced the "mostly vertical" bit: closest-hit -6 % (cfg 3) / -15 %
+// (cfg 5) against -3 % for that one; both at the price of a cell bit was worse (profiles/r2_experiments.md).
+// Boxes = roots of the BVH meshes that are small against the union of all roots (a backdrop or a room meets
+// every ray and tells nothing).  Sort key only: approximate arithmetic (MUFU reciprocal), results never depend on it.
+__device__ __forceinline__ bool RayMeetsMeshBox(const DScene& sc, float3 O, float3 D, float tmax) {
+	const float3 rD = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+	bool any = false;
+	for (int k = 0; k < sc.n_keyBoxes; k++) {
+		const float4 a = __ldg(sc.keyBoxes + 2 * k), b = __ldg(sc.keyBoxes + 2 * k + 1);
+		float tn, tx;
+		SlabApprox(f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), O, rD, tmax, tn, tx);
+		any = any || tn <= tx;
+	}
+	return any;
+}
+__device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, int areaLight = -1, bool closestQueue = false, float tmax = 3.0e38f) {
 	const int hi = (1 << AGPT_CELL_BITS) - 1;
 	int cx = min(max((int)((O.x - sc.cellLo[0]) * sc.cellScale[0]), 0), hi);
 	int cy = min(max((int)((O.y - sc.cellLo[1]) * sc.cellScale[1]), 0), hi);
@@ -84,10 +100,10 @@ __device__ __forceinline__ int RayBucket(const DScene& sc, float3 O, float3 D, i
 	int cell = 0;
 #pragma unroll
 	for (int b = 0; b < AGPT_CELL_BITS; b++) cell |= (((cx >> b) & 1) << (3 * b)) | (((cy >> b) & 1) << (3 * b + 1)) | (((cz >> b) & 1) << (3 * b + 2));
-	if (areaLight >= 0) return (cell << 4) | 8 | (areaLight & 7);
-	int code = (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
-	if (AGPT_STEEP_BIT && steep && fabsf(D.y) > fmaxf(fabsf(D.x), fabsf(D.z))) code |= 8;   // closest-hit queue: mostly-vertical rays apart
-	return (cell << 4) | code;
+	if (areaLight >= 0) return (cell << 4) | 8 | ((areaLight & 3) << 1) | (RayMeetsMeshBox(sc, O, D, tmax) ? 1 : 0);
+	const int octant = (D.x < 0.f ? 1 : 0) | (D.y < 0.f ? 2 : 0) | (D.z < 0.f ? 4 : 0);   // (octant-major order measured no better)
+	if (closestQueue) return (cell << 4) | (octant << 1) | (RayMeetsMeshBox(sc, O, D, tmax) ? 1 : 0);
+	return (cell << 4) | octant;
 }
 // ---- bucket pass between shade and the next trace: counting sort of a ray queue by key ------
 // k_bucket_hist (entries per bucket) -> k_bucket_scan (exclusive offsets, one block) ->
@@ -657,7 +673,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 						ps.shO[path] = make_float4(vis.O.x, vis.O.y, vis.O.z, vis.t);
 						ps.shD[path] = make_float4(vis.D.x, vis.D.y, vis.D.z, 0.f);
 						emitShadow = true;
-						keyShadow = RayBucket(sc, vis.O, vis.D, lightType == AGPT_LIGHT_AREA ? numLight : -1);
+						keyShadow = RayBucket(sc, vis.O, vis.D, lightType == AGPT_LIGHT_AREA ? numLight : -1, false, vis.t);
 					}
 				}
 				if (smpMis.ok) {
