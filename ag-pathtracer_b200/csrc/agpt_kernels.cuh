@@ -81,7 +81,10 @@ struct RayCounters {     // device-side totals, see agpt_stats
 // Boxes = roots of the BVH meshes that are small against the union of all roots (a backdrop or a room meets
 // every ray and tells nothing).  Sort key only: approximate arithmetic (MUFU reciprocal), results never depend on it.
 __device__ __forceinline__ bool RayMeetsMeshBox(const DScene& sc, float3 O, float3 D, float tmax) {
-	const float3 rD = f3(__frcp_rn(D.x), __frcp_rn(D.y), __frcp_rn(D.z));
+	float3 rD;        // one MUFU each: a sort key needs no more
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rD.x) : "f"(D.x));
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rD.y) : "f"(D.y));
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rD.z) : "f"(D.z));
 	bool any = false;
 	for (int k = 0; k < sc.n_keyBoxes; k++) {
 		const float4 a = __ldg(sc.keyBoxes + 2 * k), b = __ldg(sc.keyBoxes + 2 * k + 1);
