@@ -759,7 +759,7 @@ static int RunWaves(agpt_ctx* c, const DScene& scIn, PathState& ps, int n, int m
 		CU(cudaMemsetAsync(q[cur ^ 1].counts, 0, 3 * sizeof(int), c->stream));
 		if (timing) CU(cudaEventRecord(c->evC, c->stream));
 		ShadeParams sp;
-		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg; sp.rr_by_bounce = (flags & AGPT_FLAG_RR_BY_BOUNCE) ? 1 : 0;
+		sp.count = q[cur].counts + 2; sp.max_depth = max_depth; sp.rr_depth_arg = rr_depth_arg; sp.rr_by_bounce = (flags & AGPT_FLAG_RR_BY_BOUNCE) ? 1 : 0; sp.exact_counts = count ? 1 : 0;
 		// shade: k_shade_a (per active entry: NEE fold, emission, termination -> survivor list),
 		// then k_shade_b (per survivor: the BSDF work), blocks striding over the list
 		CU(cudaMemsetAsync(c->survivorCount.p, 0, sizeof(int), c->stream));

@@ -370,6 +370,7 @@ struct ShadeParams {
 	int max_depth;
 	int rr_depth_arg;     // the `depth` argument of Li (integrator.h:124,181)
 	int rr_by_bounce;     // AGPT_FLAG_RR_BY_BOUNCE: roulette keyed on the bounce index instead (extension)
+	int exact_counts;     // AGPT_FLAG_COUNTERS: rays_mis_culled must be exact, so no MIS sample is dropped before its BSDF value is known
 };
 
 // ENV: the scene has an InfiniteAreaLight; scenes without one run the leaner instantiation.
@@ -635,6 +636,26 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			}
 		}
 
+		// The BSDF-strategy sample of EstimateDirect (integrator.h:62-90) matters only if its ray can end on the chosen
+		// light: a sphere light's ray must meet that sphere (the exact MIS cull of phase E: Sphere::Intersect with the
+		// largest possible ray.t), a uniform sky needs Pdf_Li != 0 (lights.cpp:26-28).  Where it cannot, the BSDF value at
+		// that direction -- one of this vertex's three evaluations -- is never used, and is not computed.  (With
+		// AGPT_FLAG_COUNTERS it is: whether the reference would have traced the ray depends on that value being non-black.)
+		bool misUseful = true;
+		if (full && doNee && smpMis.ok && !sp.exact_counts) {
+			const float3 wim = LocalToWorld(vb.b, smpMis.wi);
+			if (lightType == AGPT_LIGHT_AREA) {
+				misUseful = false;
+				if (lightPrimType == AGPT_PRIM_SPHERE) {
+					const DRay mr = MakeRay(si.p + AGPT_EPSILON * wim, wim);
+					float tLight;
+					misUseful = SphereTest(sc.spheres[lightPayload], mr.O, mr.D, mr.t, tLight);
+				}
+			}
+			else if (!(ENV && lightType == AGPT_LIGHT_INFINITE_AREA)) misUseful = dot(si.n, wim) > 0;
+		}
+		const bool misDropped = full && doNee && smpMis.ok && !misUseful;
+
 		// ================= phase D: one evaluator, three directions (light, MIS, continuation) =================
 		float3 fLight = f3(0.f), fMis = f3(0.f), fCont = f3(0.f);
 		float pdfLight = 0.f, pdfMis = 0.f, pdfCont = 0.f;
@@ -645,7 +666,7 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 			const int sampledLobe = k == 1 ? smpMis.lobe : smpCont.lobe;
 			const float3 sampledWi = k == 1 ? smpMis.wi : smpCont.wi;
 			bool sampled = k > 0 && sampledOk;
-			bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && sampledLobe != AGPT_LOBE_SPECULAR));
+			bool need = full && (k == 0 ? (evalLight && vb.woOk) : (sampled && sampledLobe != AGPT_LOBE_SPECULAR && (k == 2 || misUseful)));
 			float3 wiLoc = k == 0 ? WorldToLocal(vb.b, wiL) : sampledWi;
 			LobeEval ev;
 			ev.f = f3(0.f); ev.pdfCos = 0.f; ev.pdfMicro = 0.f; ev.fT = f3(0.f); ev.pdfT = 0.f;
@@ -679,7 +700,10 @@ __global__ void __launch_bounds__(AGPT_SHADE_THREADS, AGPT_SHADE_MIN_BLOCKS) k_s
 						keyShadow = RayBucket(sc, vis.O, vis.D, lightType == AGPT_LIGHT_AREA ? numLight : -1, false, vis.t);
 					}
 				}
-				if (smpMis.ok) {
+				// (a dropped sphere-light sample counts as a culled ray -- an upper bound without AGPT_FLAG_COUNTERS, since a black
+				// BSDF value would not have been traced upstream either; a sky sample with Pdf_Li == 0 is no ray upstream)
+				if (misDropped) misCulled = lightType == AGPT_LIGHT_AREA && lightPrimType == AGPT_PRIM_SPHERE;
+				else if (smpMis.ok) {
 					float3 wim = wiMis;
 					float3 f = fMis;
 					scatteringPdf = pdfMis;

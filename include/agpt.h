@@ -178,7 +178,9 @@ typedef struct agpt_stats {
 	uint64_t rays_shadow;      /* any-hit visibility rays (integrator.h:50) */
 	uint64_t rays_mis;         /* closest-hit MIS rays (integrator.h:79) */
 	uint64_t rays_skip;        /* of rays_closest: continuation through null-material shapes (integrator.h:158) */
-	uint64_t rays_mis_culled;  /* MIS rays the reference traces but that provably cannot reach their light: not traced, not counted above */
+	uint64_t rays_mis_culled;  /* MIS rays the reference traces but that provably cannot reach their light: not traced, not counted above.
+	                            * Exact in renders made with AGPT_FLAG_COUNTERS; otherwise an upper bound (such samples are dropped before their BSDF
+	                            * value is known, and the reference does not trace a sample whose value is black) */
 	uint64_t rays_tail_culled; /* path rays the reference traces at bounces == MaxDepth and then discards (integrator.h:139,150): not traced, not counted above */
 	/* traversal work, only counted with AGPT_FLAG_COUNTERS; [0] closest-hit kernel, [1] any-hit kernel */
 	uint64_t node_visits[2];   /* interior sibling pairs fetched (64 B each) */

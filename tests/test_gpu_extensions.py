@@ -165,7 +165,7 @@ def test_rough_glass_scene_matches_cpu_statement(agpt, port, gpu_ctx):
     hs = agpt.HostScene(10, level); ps = port.PortScene(hs)
     ps.set_rr_by_bounce(True)
     hs.upload(gpu_ctx); gpu_ctx.set_film(W, H); gpu_ctx.clear(); gpu_ctx.reset_stats()
-    gpu_ctx.render(0, spp, d["max_depth"], 0, agpt.FLAG_RR_BY_BOUNCE)
+    gpu_ctx.render(0, spp, d["max_depth"], 0, agpt.FLAG_RR_BY_BOUNCE | agpt.FLAG_COUNTERS)      # (counting mode: exact ray accounting)
     got = gpu_ctx.read_accum()
     st = gpu_ctx.stats()
     want, cnt = ps.render(W, H, 0, spp, d["max_depth"], 0)

@@ -58,7 +58,7 @@ def test_ray_accounting_matches_reference(agpt, gpu_ctx, config, level, W, H):
     d = agpt.config_defaults(config)
     hs = agpt.HostScene(config, level); ps = port.PortScene(hs)
     hs.upload(gpu_ctx); gpu_ctx.set_film(W, H); gpu_ctx.clear(); gpu_ctx.reset_stats()
-    gpu_ctx.render(0, 2, d["max_depth"], d["depth_arg"])
+    gpu_ctx.render(0, 2, d["max_depth"], d["depth_arg"], agpt.FLAG_COUNTERS)      # exact ray accounting needs the counting mode (agpt.h: rays_mis_culled)
     st = gpu_ctx.stats()
     _, cnt = ps.render(W, H, 0, 2, d["max_depth"], d["depth_arg"])
     assert st.rays_shadow == cnt["rays_any"]
