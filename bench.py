@@ -502,7 +502,8 @@ def main():
     e2e_value = e2e_rays / e2e_s / 1e6
 
     # ---- roofline of the dominant kernel + counters (rank 0, extra untimed steps) --------
-    roofline = roofline_issue = l2_side = breakdown = per_bounce = None
+    roofline = roofline_issue = l2_side = breakdown = per_bounce = counting_step = None
+    ref_eq_ratio = rays_ref_eq / max(rays, 1.0)
     if rank == 0:
         ctx.clear()
         ctx.reset_stats()
@@ -511,6 +512,9 @@ def main():
         ctx.reset_stats()
         step(args.warmup + args.steps, pkg.FLAG_COUNTERS)
         cn = ctx.stats()
+        ref_eq_ratio = cn.rays_reference_equivalent / max(cn.rays, 1)
+        counting_step = {"traced": float(cn.rays), "mis_culled_exactly": float(cn.rays_mis_culled), "tail_culled_exactly": float(cn.rays_tail_culled),
+                         "reference_equivalent": float(cn.rays_reference_equivalent)}
         per_bounce = per_bounce_table(ctx, 0)
         peak, peak_src = measured_peak_gbs()
         l2_gbs = ctx.probe_bandwidth(32 << 20, 200)            # 32 MB, L2-resident: what a streaming read gets out of L2
@@ -662,9 +666,11 @@ def main():
                # outcome cannot matter (MIS rays that miss their light's sphere, the discarded ray at MaxDepth);
                # the B200 path proves them useless and skips them, so spp/s is the like-for-like speed and
                # ref_equivalent_Mrays_per_s is the throughput in the reference's own ray accounting.
-               "ref_equivalent_Mrays_per_s": rays_ref_eq / ms_max / 1e3,
-               "rays": {"closest_path": r_closest, "shadow": r_shadow, "mis_traced": r_mis, "mis_culled_exactly": r_mis_culled,
-                        "tail_culled_exactly": r_tail_culled},
+               # (The culled counts are exact only in a counting render -- agpt.h, rays_mis_culled -- so the ratio reference rays /
+               # traced rays comes from the untimed AGPT_FLAG_COUNTERS step of this same workload and scales the measured value.)
+               "ref_equivalent_Mrays_per_s": value * ref_eq_ratio,
+               "rays": {"closest_path": r_closest, "shadow": r_shadow, "mis_traced": r_mis, "mis_not_traced_upper_bound": r_mis_culled,
+                        "tail_culled_exactly": r_tail_culled, "counting_step": counting_step},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "api": e2e_api, "steps": e2e_steps, "rays_counted": e2e_rays, "seconds": e2e_s},

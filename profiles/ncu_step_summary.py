@@ -57,6 +57,12 @@ def main(csv_path, stats_path, out_path):
                           ("fma_pipe", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"), ("alu_pipe", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active")):
             a[key + "_x_ms"] += m.get(name, 0.0) * t          # time-weighted
     stats = json.load(open(stats_path))
+    # the ray counts must be those of the CAPTURED run: ncu_target.py writes them during the capture, and any later run of
+    # it overwrites the file (round 2 shipped a summary whose counts came from a 4-spp run beside a 16-spp capture)
+    for kname, key in (("k_trace_closest", "launches_closest"), ("k_trace_any", "launches_any")):
+        seen = int(agg[kname]["launches"]) if kname in agg else 0
+        if seen != int(stats[key]):
+            sys.exit(f"{stats_path} does not belong to {csv_path}: {kname} launched {seen} times in the capture, {stats[key]} in the stats file")
     units = {"k_trace_closest": stats["rays_closest_kernel"], "k_trace_any": stats["rays_any_kernel"], "k_shade_a": stats["rays_closest_kernel"],
              "k_shade_b": stats["rays_closest_kernel"]}
     total_ms = sum(a["ms"] for a in agg.values())

@@ -17,4 +17,4 @@ os.makedirs('gpurun_out', exist_ok=True)
 json.dump({"config": cfg, "level": level, "spp": spp, "width": d['width'], "height": d['height'], "paths": s.paths,
            "rays_closest_kernel": s.rays_closest + s.rays_mis, "rays_any_kernel": s.rays_shadow, "waves": s.waves,
            "launches_closest": s.launches_closest, "launches_any": s.launches_any, "launches_shade": s.launches_shade, "ms_render": s.ms_render},
-          open('gpurun_out/ncu_target_stats.json', 'w'))
+          open(os.environ.get('AGPT_NCU_STATS', 'gpurun_out/ncu_target_stats.json'), 'w'))
