@@ -236,6 +236,12 @@ class Context:
         assert arr.shape == (self.height, self.width, 4)
         _check(core().agpt_write_accum(self._h, _fptr(arr)))
 
+    def write_accum_begin(self, arr):
+        """agpt_write_accum_begin: the upload runs beside the render that follows; `arr` (C-contiguous float32, ideally
+        page-locked: pinned_film) must stay untouched until the next call that touches the film returns."""
+        assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"] and arr.shape == (self.height, self.width, 4)
+        _check(core().agpt_write_accum_begin(self._h, _fptr(arr)))
+
     def accum_ptr(self):
         p = c_void_p()
         _check(core().agpt_accum_ptr_dev(self._h, byref(p)))

@@ -59,6 +59,9 @@ struct agpt_ctx {
 	int device = 0;
 	cudaStream_t ownStream = nullptr, stream = nullptr;
 	cudaStream_t sideStream = nullptr;   // any-hit trace of a wave runs here, beside the closest-hit trace
+	cudaStream_t copyStream = nullptr;   // agpt_write_accum_begin: the film upload runs here, beside the render that follows
+	cudaEvent_t evUpload = nullptr;
+	bool uploadPending = false;          // a film upload is in flight: k_accumulate waits for it, every other film access joins it first
 	cudaEvent_t evFork = nullptr, evJoin = nullptr;
 	cudaEvent_t evA = nullptr, evB = nullptr, evC = nullptr, evD = nullptr;
 	cudaEvent_t evRender0 = nullptr, evRender1 = nullptr;      // bracket of agpt_render (ms_render)
@@ -289,6 +292,17 @@ static int CheckReady(agpt_ctx* c, bool needFilm) {
 
 static inline int Blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
+// A film upload started by agpt_write_accum_begin may still be in flight: whatever touches the film next waits for it.
+static int JoinUpload(agpt_ctx* c) {
+	if (c != nullptr && c->uploadPending) {
+		CU(cudaSetDevice(c->device));
+		CU(cudaStreamSynchronize(c->copyStream));
+		c->uploadPending = false;
+	}
+	return AGPT_OK;
+}
+#define JOIN(c) do { int j_ = JoinUpload(c); if (j_ != AGPT_OK) return j_; } while (0)
+
 // ---- launch helpers: template flags from run-time flags --------------------------------------
 // (COUNT, FAST = !strictBoxes, INST = the scene has instances) -> one of eight instantiations
 #define AGPT_DISPATCH3(count, fast, inst, CALL) do { \
@@ -345,6 +359,8 @@ int agpt_create(int device, agpt_ctx** out) {
 	CU(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
 	c->stream = c->ownStream;
 	CU(cudaStreamCreateWithFlags(&c->sideStream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->evUpload, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
 	CU(cudaEventCreate(&c->evA)); CU(cudaEventCreate(&c->evB)); CU(cudaEventCreate(&c->evC)); CU(cudaEventCreate(&c->evD));
 	CU(cudaEventCreate(&c->evRender0)); CU(cudaEventCreate(&c->evRender1));
@@ -368,6 +384,7 @@ int agpt_create(int device, agpt_ctx** out) {
 }
 
 int agpt_destroy(agpt_ctx* c) {
+	JOIN(c);
 	if (!c) return AGPT_OK;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
@@ -390,6 +407,8 @@ int agpt_destroy(agpt_ctx* c) {
 	cudaEventDestroy(c->evRender0); cudaEventDestroy(c->evRender1);
 	cudaEventDestroy(c->evFork); cudaEventDestroy(c->evJoin);
 	cudaStreamDestroy(c->sideStream);
+	cudaStreamDestroy(c->copyStream);
+	cudaEventDestroy(c->evUpload);
 	cudaStreamDestroy(c->ownStream);
 	delete c;
 	return AGPT_OK;
@@ -556,6 +575,7 @@ int agpt_set_camera(agpt_ctx* c, const agpt_camera* cam) {
 }
 
 int agpt_set_film(agpt_ctx* c, int width, int height) {
+	JOIN(c);
 	NEED(c != nullptr && width > 0 && height > 0 && (long long)width * height < (1ll << 30), AGPT_ERR_INVALID, "bad film size");
 	CU(cudaSetDevice(c->device));
 	if (width == c->width && height == c->height) return AGPT_OK;
@@ -580,17 +600,20 @@ int agpt_scene_bytes(agpt_ctx* c, uint64_t* out) {
 
 // ---- accumulator -------------------------------------------------------------------------
 int agpt_clear(agpt_ctx* c) {
+	JOIN(c);
 	NEED(c != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
 	CU(cudaSetDevice(c->device));
 	CU(cudaMemsetAsync(c->accum, 0, (size_t)c->width * c->height * sizeof(float4), c->stream));
 	return AGPT_OK;
 }
 int agpt_accum_ptr_dev(agpt_ctx* c, void** p) {
+	JOIN(c);
 	NEED(c != nullptr && p != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
 	*p = c->accum;
 	return AGPT_OK;
 }
 int agpt_set_accum_dev(agpt_ctx* c, void* p) {
+	JOIN(c);
 	NEED(c != nullptr, AGPT_ERR_INVALID, "null context");
 	NEED(c->width > 0, AGPT_ERR_STATE, "film not set");
 	CU(cudaSetDevice(c->device));
@@ -603,6 +626,7 @@ int agpt_set_accum_dev(agpt_ctx* c, void* p) {
 	return AGPT_OK;
 }
 int agpt_read_accum(agpt_ctx* c, float* host) {
+	JOIN(c);
 	NEED(c != nullptr && host != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
 	CU(cudaSetDevice(c->device));
 	CU(cudaMemcpyAsync(host, c->accum, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
@@ -610,13 +634,27 @@ int agpt_read_accum(agpt_ctx* c, float* host) {
 	return AGPT_OK;
 }
 int agpt_write_accum(agpt_ctx* c, const float* host) {
+	JOIN(c);
 	NEED(c != nullptr && host != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
 	CU(cudaSetDevice(c->device));
 	CU(cudaMemcpyAsync(c->accum, host, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	return AGPT_OK;
 }
+int agpt_write_accum_begin(agpt_ctx* c, const float* host) {
+	JOIN(c);
+	NEED(c != nullptr && host != nullptr && c->accum != nullptr, AGPT_ERR_STATE, "film not set");
+	CU(cudaSetDevice(c->device));
+	// everything queued on the render stream so far (a clear, an earlier render's accumulate) comes first
+	CU(cudaEventRecord(c->evUpload, c->stream));
+	CU(cudaStreamWaitEvent(c->copyStream, c->evUpload, 0));
+	CU(cudaMemcpyAsync(c->accum, host, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyHostToDevice, c->copyStream));
+	CU(cudaEventRecord(c->evUpload, c->copyStream));
+	c->uploadPending = true;
+	return AGPT_OK;
+}
 int agpt_resolve(agpt_ctx* c, int samples, uint32_t* host) {
+	JOIN(c);
 	NEED(c != nullptr && host != nullptr && c->accum != nullptr && samples > 0, AGPT_ERR_STATE, "film not set or samples <= 0");
 	CU(cudaSetDevice(c->device));
 	int n = c->width * c->height;
@@ -854,12 +892,14 @@ int agpt_render(agpt_ctx* c, int first_sample, int num_samples, int sample_strid
 		c->stats.rays_closest += (uint64_t)n;     // camera rays; the rest is counted on the device
 		rcode = RunWaves(c, sc, ps, n, max_depth, rr_depth_arg, flags);
 		if (rcode != AGPT_OK) return rcode;
+		if (c->uploadPending) CU(cudaStreamWaitEvent(c->stream, c->evUpload, 0));      // the film this batch adds to may still be on its way (agpt_write_accum_begin)
 		k_accumulate<<<Blocks(wh, 256), 256, 0, c->stream>>>(ps.Lout, c->accum, c->width, c->height, ns);
 		CU(cudaGetLastError());
 		c->stats.kernel_launches++;
 	}
 	CU(cudaEventRecord(r1, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
+	c->uploadPending = false;        // k_accumulate waited for it
 	float ms = 0;
 	cudaEventElapsedTime(&ms, r0, r1);
 	c->stats.ms_render += ms;
@@ -990,6 +1030,7 @@ int agpt_li_rays(agpt_ctx* c, int n, const float* rays7, const uint32_t* rng_sta
 // ---- multi-GPU: sample-index sharding ---------------------------------------------
 // One context per GPU, every context holds the whole scene; GPU g renders s = first + g, first + g + G, ...
 static int CheckGroup(agpt_ctx** ctxs, int n) {
+	for (int g = 0; ctxs != nullptr && g < n; g++) JOIN(ctxs[g]);
 	NEED(ctxs != nullptr && n >= 1 && n <= AGPT_MAX_PEERS, AGPT_ERR_INVALID, "bad context list (1.." + std::to_string(AGPT_MAX_PEERS) + " contexts)");
 	for (int g = 0; g < n; g++) {
 		NEED(ctxs[g] != nullptr && ctxs[g]->accum != nullptr, AGPT_ERR_STATE, "context " + std::to_string(g) + ": film not set");
@@ -1168,6 +1209,7 @@ int agpt_render_multi(agpt_ctx** ctxs, int n, int first_sample, int num_samples,
 
 // ---- multi-process sharding (one rank per GPU: torchrun, MPI): peers' accumulators through CUDA IPC ----
 int agpt_accum_ipc_handle(agpt_ctx* c, void* handle64) {
+	JOIN(c);
 	NEED(c != nullptr && handle64 != nullptr, AGPT_ERR_INVALID, "null argument");
 	NEED(c->accum != nullptr && c->accum == c->accumOwn.p, AGPT_ERR_STATE, "the context must own its accumulator (agpt_set_film, no agpt_set_accum_dev)");
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1189,6 +1231,7 @@ int agpt_close_peer_accums(agpt_ctx* c) {
 }
 
 int agpt_open_peer_accums(agpt_ctx* c, int rank, int world, const void* handles64) {
+	JOIN(c);
 	NEED(c != nullptr && handles64 != nullptr && world >= 1 && world <= AGPT_MAX_PEERS && rank >= 0 && rank < world, AGPT_ERR_INVALID, "bad rank / world / handles");
 	NEED(c->accum != nullptr, AGPT_ERR_STATE, "film not set");
 	int rcode = agpt_close_peer_accums(c);
@@ -1217,6 +1260,7 @@ static int PeerTable(agpt_ctx* c, PeerAccums* pa) {
 // This rank's slice of the all-reduce.  The CALLER provides the two barriers: every rank has finished
 // rendering before any rank calls, and no rank reads its accumulator before every rank has returned.
 int agpt_allreduce_accum_peers(agpt_ctx* c) {
+	JOIN(c);
 	PeerAccums pa;
 	int rcode = PeerTable(c, &pa);
 	if (rcode != AGPT_OK) return rcode;
@@ -1239,6 +1283,7 @@ int agpt_allreduce_accum_peers(agpt_ctx* c) {
 // host; keep_sum != 0 also stores the sum in this rank's accumulator.  Reads the peers, writes none of them:
 // only the barrier BEFORE the call is needed.
 int agpt_reduce_resolve_peers(agpt_ctx* c, int samples, int keep_sum, uint32_t* host_rgb8) {
+	JOIN(c);
 	PeerAccums pa;
 	int rcode = PeerTable(c, &pa);
 	if (rcode != AGPT_OK) return rcode;

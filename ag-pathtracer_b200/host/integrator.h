@@ -100,7 +100,7 @@ protected:
 		for (size_t g = 0; g < ctxs.size(); g++) {
 			Check(agpt_set_camera(ctxs[g], &cam));
 			Check(agpt_set_film(ctxs[g], acc.width, acc.height));
-			if (g == 0) Check(agpt_write_accum(ctxs[g], &acc.Pixels()->x));
+			if (g == 0) Check(agpt_write_accum_begin(ctxs[g], &acc.Pixels()->x));      // lands while the batch is traced; k_accumulate waits for it
 			else Check(agpt_clear(ctxs[g]));
 		}
 		if (ctxs.size() == 1) Check(agpt_render(ctxs[0], firstSample, numSamples, 1, MaxDepth, depth, flags));

@@ -475,7 +475,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for k in range(e2e_steps):
-            ctx.write_accum(host_acc)                                   # every rank: its host film -> device
+            ctx.write_accum_begin(host_acc)                             # every rank: its host film -> device, beside the render below
             pkg.multigpu.render_sharded(ctx, (1 + k) * spp_all, spp_all, depth, depth_arg, rank, world)
             if route.startswith("peer"):
                 light_barrier(sync=False)
@@ -492,7 +492,7 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_rays = float(ctx.stats().rays)
-        e2e_api = "C ABI, one process per GPU: agpt_write_accum + agpt_render(stride N) on every rank, agpt_reduce_resolve_peers + agpt_read_accum on the root"
+        e2e_api = "C ABI, one process per GPU: agpt_write_accum_begin + agpt_render(stride N) on every rank, agpt_reduce_resolve_peers + agpt_read_accum on the root"
         h2d, d2h = world * W * H * 16, W * H * 16 + W * H * 4
     e2e_t = torch.tensor([e2e_s, e2e_rays], dtype=torch.float64, device=dev)
     if world > 1:

@@ -274,6 +274,11 @@ int agpt_accum_ptr_dev(agpt_ctx* ctx, void** dev_ptr);          /* float4[W*H] i
 int agpt_set_accum_dev(agpt_ctx* ctx, void* dev_ptr);           /* accumulate into caller-owned device memory */
 int agpt_read_accum(agpt_ctx* ctx, float* host_rgba);           /* D2H of float4[W*H] */
 int agpt_write_accum(agpt_ctx* ctx, const float* host_rgba);    /* H2D (resume) */
+/* The same upload, started and not waited for: it runs beside the agpt_render that follows (the film is only needed when a
+ * batch is added to it, at the end) -- the batched Tick of CudaPathTracer::Render hides its H2D copy this way.  The host buffer
+ * must stay untouched until the next call on this context that reads or writes the film returns (agpt_render, agpt_read_accum,
+ * agpt_resolve, the reduce calls ...: each waits for the upload first).  Page-locked memory (agpt_host_alloc) for a true overlap. */
+int agpt_write_accum_begin(agpt_ctx* ctx, const float* host_rgba);
 /* Accumulator::CopyToSurface (myapp.h:34-41): /samples, pow(1/2.2), 8-bit pack 0x00RRGGBB. */
 int agpt_resolve(agpt_ctx* ctx, int samples, uint32_t* host_rgb8);
 

@@ -91,3 +91,23 @@ def test_sphere_run_cull_is_exact(agpt, ref, gpu_ctx):
             assert np.array_equal(got["prim"], want["prim"])
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
     assert 0.2 < want["found"].mean() < 1.0
+
+
+def test_write_accum_begin_equals_write_accum(agpt, gpu_ctx):
+    """agpt_write_accum_begin (the film upload that runs beside the render that follows) gives the frame agpt_write_accum
+    gives, bit for bit; a film access without a render in between waits for the upload too."""
+    d = agpt.config_defaults(1)
+    W, H = 320, 180
+    hs = agpt.HostScene(1, 0); hs.upload(gpu_ctx); gpu_ctx.set_film(W, H)
+    film, owner = agpt.pinned_film(W, H)
+    film[:] = np.random.default_rng(5).random((H, W, 4), dtype=np.float32)
+    gpu_ctx.write_accum(film.copy()); gpu_ctx.render(0, 3, d["max_depth"], d["depth_arg"]); want = gpu_ctx.read_accum()
+    gpu_ctx.clear()
+    gpu_ctx.write_accum_begin(film); gpu_ctx.render(0, 3, d["max_depth"], d["depth_arg"]); got = gpu_ctx.read_accum()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    gpu_ctx.clear()
+    gpu_ctx.write_accum_begin(film)
+    assert np.array_equal(gpu_ctx.read_accum().view(np.uint32), film.view(np.uint32))
+    gpu_ctx.write_accum_begin(film); gpu_ctx.clear()
+    assert not gpu_ctx.read_accum().any()
+    del owner
