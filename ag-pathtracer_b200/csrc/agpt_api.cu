@@ -48,11 +48,13 @@ struct MeshStore {
 };
 
 #ifndef AGPT_BATCH_LOG2
-#define AGPT_BATCH_LOG2 25
+#define AGPT_BATCH_LOG2 27
 #endif
-// Paths in flight per batch.  2^25 = 33.5 M slots ~ 8.5 GB of wavefront state + queues (sized for 180 GB of
-// HBM3e).  Bigger batches mean fuller waves and more rays per bucket, i.e. more coherent warps: cfg 3 at
-// 16 spp runs in 106 / 98 / 94 ms with 2^23 / 2^24 / 2^25 slots.
+// Paths in flight per batch, at most.  2^27 = 134 M slots ~ 39 GB of wavefront state + queues (sized for 180 GB of
+// HBM3e; the state is allocated for the batches a caller actually asks for: 16 spp at 1080p take 33 M slots).
+// Bigger batches mean fuller waves and more rays per bucket, i.e. more coherent warps: cfg 3 runs a 16-spp
+// share in 106 / 98 / 94 ms with batches of 2^23 / 2^24 / 2^25 slots (round 1's kernels) and in 57.9 / 55.8 /
+// 54.4 ms with 2^25 / 2^26 / 2^27 (16 / 32 / 64 spp per batch at 1080p, round 2's).
 static const size_t kMaxPathsPerBatch = (size_t)1 << AGPT_BATCH_LOG2;
 
 struct agpt_ctx {

@@ -8,7 +8,10 @@ rank per GPU) prints ONE JSON line from rank 0.
   8 bounces"): Disney multi-material scene, 1.31 M triangles in BVHTriMesh objects + 25
   analytic spheres + backdrop + floor, three sphere area lights + uniform sky, NEE + MIS,
   PathTracer(8), 1920x1080, 256 spp.  A STEP is one batch of `--spp-per-step` samples per
-  pixel per GPU (16 -> 16 steps make the configuration's 256 spp on one GPU).  `--config
+  pixel per GPU (default 64 = one full wavefront batch of 2^27 path slots at 1080p: four steps make the
+  configuration's 256 spp on one GPU; bigger batches are fuller waves and more coherent ray buckets --
+  16 / 32 / 64 spp per batch take 57.9 / 55.8 / 54.4 ms per 16 spp; `ms_per_16spp` keeps the figure of
+  the earlier rounds comparable).  `--config
   {2,3,4,5}` times another BASELINE configuration instead; the default run also carries a
   short measurement of cfg 2, 4 and 5 in `other_configs` (cfg 4 = the multi-GPU configuration:
   at N > 1 a FIXED total of samples is split over the ranks -- strong scaling -- with the
@@ -245,7 +248,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU renders --spp-per-step samples per step; strong: --spp-per-step samples per step in TOTAL, split over the GPUs")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="accumulator exchange at N > 1: this library's peer-memory kernel, or torch.distributed NCCL")
-    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--spp-per-step", type=int, default=64)
     ap.add_argument("--level", type=int, default=0, help="icosphere subdivision override (tests); 0 = the configuration's own")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
@@ -658,7 +661,7 @@ def main():
     if rank == 0:
         cfg_obj = bench_config(CFG, world, spp_step, args.level, args.width, args.height)
         out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+               "ms_per_step": ms_max / args.steps, "ms_per_16spp": ms_max / args.steps * 16.0 / spp_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": cfg_obj,
                "scene": {"bvh_nodes": counts["nodes"], "primitives": counts["prims"], "lights": counts["lights"], "scene_bytes": counts["bytes"]},
                "spp_per_s": paths / (W * H) / (ms_max * 1e-3), "Mpaths_per_s": paths / ms_max / 1e3,
