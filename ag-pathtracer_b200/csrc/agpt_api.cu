@@ -386,7 +386,7 @@ int agpt_create(int device, agpt_ctx** out) {
 }
 
 int agpt_destroy(agpt_ctx* c) {
-	JOIN(c);
+	JoinUpload(c);          // (an upload still in flight must not outlive its buffers; a failure here changes nothing about what follows)
 	if (!c) return AGPT_OK;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);

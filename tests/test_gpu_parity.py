@@ -111,3 +111,45 @@ def test_write_accum_begin_equals_write_accum(agpt, gpu_ctx):
     gpu_ctx.write_accum_begin(film); gpu_ctx.clear()
     assert not gpu_ctx.read_accum().any()
     del owner
+
+
+@pytest.mark.parametrize("config,level,W,H,depth", [(1, 0, 157, 83, None), (6, 2, 157, 83, None), (1, 0, 1, 1, None), (6, 2, 9, 5, None),
+                                                      (3, 2, 24, 11, 0), (3, 2, 40, 12, 1), (7, 0, 33, 17, None)])
+def test_ragged_and_tiny_films(agpt, gpu_ctx, config, level, W, H, depth):
+    """Films that are not a multiple of the 8x4 path-slot tile (row-major slot order), a 1x1 film, depth 0 (emission only)
+    and depth 1: bit-identical to the restatement (itself pinned bit for bit to the reference), sample ranges that do not
+    start at 0 included."""
+    from oracle import port_binding as port
+    d = agpt.config_defaults(config)
+    depth = d["max_depth"] if depth is None else depth
+    hs = agpt.HostScene(config, level); ps = port.PortScene(hs)
+    hs.upload(gpu_ctx); gpu_ctx.set_film(W, H); gpu_ctx.clear()
+    gpu_ctx.render(3, 5, depth, d["depth_arg"])
+    got = gpu_ctx.read_accum()
+    want, _ = ps.render(W, H, 3, 5, depth, d["depth_arg"])
+    assert np.array_equal(got[..., :3].view(np.uint32), want[..., :3].view(np.uint32))
+
+
+def test_batches_do_not_change_the_film(agpt):
+    """A render split into many wavefront batches (the batch cap far below samples x pixels) and the same render in one
+    batch give the same film: every path's arithmetic depends on its pixel and sample only."""
+    import os
+    d = agpt.config_defaults(3)
+    hs = agpt.HostScene(3, 3)
+    films = []
+    for log2 in ("27", "16", "12"):           # 6, 3 and 1 samples per batch (the cap never cuts below one sample of the film)
+        old = os.environ.get("AGPT_BATCH_LOG2")
+        os.environ["AGPT_BATCH_LOG2"] = log2
+        try:
+            ctx = agpt.Context(0)
+        finally:
+            if old is None:
+                os.environ.pop("AGPT_BATCH_LOG2", None)
+            else:
+                os.environ["AGPT_BATCH_LOG2"] = old
+        hs.upload(ctx); ctx.set_film(200, 100)
+        ctx.render(0, 6, d["max_depth"], d["depth_arg"])
+        films.append(ctx.read_accum())
+        ctx.close()
+    assert np.array_equal(films[0].view(np.uint32), films[1].view(np.uint32))
+    assert np.array_equal(films[0].view(np.uint32), films[2].view(np.uint32))
