@@ -581,7 +581,9 @@ def main():
             else:
                 octx = pkg.Context(local_rank); octx.set_stream(stream.cuda_stream); osc.upload(octx); octx.set_film(od["width"], od["height"]); octx.clear()
                 oroute = "single GPU"
-            total_spp = 16
+            # one frame = a FIXED number of samples per pixel in total (strong scaling at N > 1).  cfg 4 (4K): 128 = 16 per rank at
+            # N = 8, i.e. one full wavefront batch of 2^27 paths per GPU and an eighth of the configuration's 1024 spp; cfg 2 / 5: 64
+            total_spp = 128 if oc == 4 else 64
             nranks = world if multi else 1
             me = rank if multi else 0
 
