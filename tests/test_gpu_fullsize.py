@@ -118,11 +118,11 @@ def test_cfg1_whole_frame_at_its_own_size(agpt, ref, ctx2):
     assert np.array_equal(ctx2.resolve(spp), ref.resolve(got, spp))
 
 
-def test_cfg3_whole_frame_full_size(agpt, ref, ctx2):
+@pytest.mark.parametrize("cfg,spp", [(3, 2), (5, 1), (2, 2)])
+def test_whole_frame_full_size(agpt, ref, ctx2, cfg, spp):
     """The bench workload itself -- cfg 3 at 1920x1080, 8 bounces, 1.31 M triangles -- WHOLE film, 2 spp (4.1 M
     reference paths: about a second on the box's cores), same streams: every pixel of the B200 film against the
-    reference CPU integrator."""
-    cfg, spp = 3, 2
+    reference CPU integrator.  Likewise the closed room of cfg 5 (16 bounces, roulette live) and cfg 2."""
     d = agpt.config_defaults(cfg)
     W, H, md, da = d["width"], d["height"], d["max_depth"], d["depth_arg"]
     hs = agpt.HostScene(cfg, 0); rs = ref.RefScene(cfg, 0)
@@ -133,7 +133,7 @@ def test_cfg3_whole_frame_full_size(agpt, ref, ctx2):
     assert paths == W * H * spp
     exact = np.mean(np.all(bits(got[..., :3]) == bits(want[..., :3]), axis=-1))
     err = float(np.sqrt(np.mean((got[..., :3].astype(np.float64) - want[..., :3].astype(np.float64)) ** 2)) / np.mean(np.abs(want[..., :3])))
-    print(f"cfg3 1920x1080x{spp}: rel-RMSE {err:.3e}, bit-identical pixels {exact:.6f}")
+    print(f"cfg{cfg} 1920x1080x{spp}: rel-RMSE {err:.3e}, bit-identical pixels {exact:.6f}")
     assert err <= 1e-3
     assert exact >= 0.9999
 
